@@ -1,0 +1,101 @@
+"""The oracle against the committed golden vectors (generated from the
+unmodified reference by oracle/make_golden.py) and, when the reference tree is
+present (build container only), against the live reference."""
+import hashlib
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from conftest import GOLDEN_DIR, golden_names
+from oracle import live_reference, wm_oracle as O
+
+ARRAY_CASES = [n for n in golden_names() if not n.startswith("pil_")]
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("name", ARRAY_CASES)
+def test_oracle_embed_extract_matches_reference_vectors(golden, name):
+    g = golden(name)
+    out = O.embed_array(g["rgb"], g["wm"], 0.1, 8)
+    assert np.array_equal(out, g["ref_out"])
+    if g["wm"].size:
+        ext = O.extract_array(g["ref_out"], g["rgb"], 0.1, 8)
+        assert np.array_equal(ext, g["ref_ext"])
+    assert np.array_equal(O.rgb_to_ycbcr(g["rgb"]), g["ref_ycc"])
+
+
+@pytest.mark.parametrize("name", ["gv1_random64", "natural_ragged_70x93", "flat_black16"])
+def test_oracle_loop_style_is_identical(golden, name):
+    g = golden(name)
+    assert np.array_equal(O.embed_array(g["rgb"], g["wm"], 0.1, 8, style="loop"), g["ref_out"])
+    assert np.array_equal(O.extract_array(g["ref_out"], g["rgb"], 0.1, 8, style="loop"), g["ref_ext"])
+
+
+def test_manifest_hashes_and_survey_kats(golden):
+    man = json.load(open(os.path.join(GOLDEN_DIR, "MANIFEST.json")))
+    for name, rec in man["cases"].items():
+        g = golden(name)
+        assert _sha(g["ref_out"]) == rec["sha_out"]
+        assert _sha(g["ref_ext"]) == rec["sha_ext"]
+        assert all(v for k, v in rec.items() if k.startswith("oracle_"))
+    assert man["colour_forward_exhaustive"]["mismatching_values"] == 0
+    assert man["colour_inverse_sampled"]["mismatching_values"] == 0
+    # GV1 hashes and taps recorded by the surveyor from the live reference
+    g = golden("gv1_random64")
+    assert _sha(g["ref_out"]) == "08bbb85f1a25aa9e2aaa2bed8784c2d2adf201fd8cbcec86004b772ff3833b82"
+    assert _sha(g["ref_ext"]) == "94ba1cb4f23d2d89017310f3580aeb8ddeace3c1f3c5263619a37a9715053c07"
+    assert np.allclose(g["ref_ycc"][0, :4, 0], [0.4973765, 0.83600783, 0.4075608, 0.8097412], rtol=0, atol=1e-7)
+    assert np.allclose(g["ref_S"][0, 0], [4.0165367, 0.895417, 0.70977336, 0.49719533, 0.45117784,
+                                          0.35321367, 0.17474262, 0.03545346], rtol=0, atol=1e-6)
+    assert list(g["wm"][0]) == [172, 58, 128, 244, 51, 190, 198, 77]
+    assert list(g["ref_ext"][0]) == [131, 0, 77, 201, 0, 152, 158, 36]
+    # KAT-flat: black -> 3 / extracted 239, gray 128 -> 131 / 239, white stays 255 / 0
+    for name, pix, ext in (("flat_black16", 3, 239), ("flat_gray16", 131, 239), ("flat_white16", 255, 0)):
+        g = golden(name)
+        assert (g["ref_out"] == pix).all() and (g["ref_ext"] == ext).all()
+    # KAT-zero-wm: colour round trip only moves pixels by -1/0
+    g = golden("zero_wm_32")
+    d = g["ref_out"].astype(int) - g["rgb"].astype(int)
+    assert set(np.unique(d)) <= {-1, 0}
+
+
+@pytest.mark.parametrize("name", ["pil_png_preserve1", "pil_png_preserve0"])
+def test_oracle_pil_api_with_png_bytes(golden, name):
+    g = golden(name)
+    png = g["png"].tobytes()
+    pr = name.endswith("1")
+    out = O.embed_watermark(Image.fromarray(g["rgb"]), png, pr, {"block_size": 8, "alpha": 0.1})
+    assert out.mode == "RGB" and np.array_equal(np.array(out), g["ref_out"])
+    assert np.array_equal(np.array(O.resize_watermark(png, 16, 25, pr)), g["wm"])
+    ext = O.extract_watermark(out, Image.fromarray(g["rgb"]), {"block_size": 8, "alpha": 0.1})
+    assert ext.mode == "L" and ext.size == (25, 16) and np.array_equal(np.array(ext), g["ref_ext"])
+
+
+def test_fma64_is_exact_against_rationals():
+    from fractions import Fraction as F
+    rng = np.random.default_rng(3)
+    a, b, c = rng.normal(size=(3, 2000))
+    c *= 1e-3
+    got = O.fma64(a, b, c)
+    want = np.array([float(F(x) * F(y) + F(z)) for x, y, z in zip(a, b, c)])
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.skipif(not live_reference.available(), reason="reference tree only exists in the build container")
+def test_oracle_against_live_reference_fresh_input():
+    R = live_reference.load()
+    rng = np.random.default_rng(99)
+    rgb = rng.integers(0, 256, (40, 56, 3), dtype=np.uint8)
+    wm = rng.integers(0, 256, (5, 7), dtype=np.uint8)
+    s = {"block_size": 8, "alpha": 0.1}
+    ref = np.array(R.embed_watermark(Image.fromarray(rgb), Image.fromarray(wm), False, dict(s)))
+    assert np.array_equal(O.embed_array(rgb, wm), ref)
+    ref_e = np.array(R.extract_watermark(Image.fromarray(ref), Image.fromarray(rgb), dict(s)))
+    assert np.array_equal(O.extract_array(ref, rgb), ref_e)

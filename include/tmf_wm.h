@@ -1,0 +1,102 @@
+/* libtmfwm - B200 (sm_100a) DCT+SVD watermark embed / extract.  C ABI.
+ *
+ * Drop-in boundary for the hot path of Rigelyon/ThatsMyFace
+ * `modules/watermarking.py`.  The reference is pure Python, so there is no FFI
+ * in it to mirror; these entry points are what a ctypes binding placed inside
+ * the reference's two public functions calls:
+ *
+ *   embed_watermark()   modules/watermarking.py:135-221  -> tmf_embed_rgb8
+ *   extract_watermark() modules/watermarking.py:224-294  -> tmf_extract_rgb8
+ *   rgb_to_ycbcr()      :23-50                           -> tmf_rgb8_to_ycbcr_f32
+ *   ycbcr_to_rgb()      :53-73                           -> tmf_ycbcr_f32_to_rgb8
+ *   apply_dct_to_block / apply_idct_to_block :76-83      -> tmf_dct8x8_f32
+ *   np.linalg.svd(block, full_matrices=True) :195,:279   -> tmf_svd8x8_f32
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless the
+ *     function name ends in `_host`;
+ *   - images are interleaved 8-bit RGB, rows tightly packed (3*w bytes),
+ *     image k of a batch starts at `base + k*img_stride` bytes;
+ *   - the caller owns every buffer; the library allocates nothing persistent
+ *     and keeps no reference after the call's work on `stream` has completed;
+ *   - `stream` is a cudaStream_t (NULL = default stream); calls are
+ *     asynchronous with respect to the host and re-entrant;
+ *   - return value 0 = OK, negative = error (enum below); a description of the
+ *     last error on the calling thread is available from tmf_last_error();
+ *   - there is no CPU fallback: without a usable CUDA device every compute
+ *     entry point returns TMF_ERR_CUDA.
+ */
+#ifndef TMF_WM_H
+#define TMF_WM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMF_VERSION 100 /* 0.1.0 */
+
+enum {
+  TMF_OK = 0,
+  TMF_ERR_BAD_ARG = -1,           /* null pointer, negative size, bad stride, bad mode */
+  TMF_ERR_UNSUPPORTED_BLOCK = -2, /* block_size other than 8 (the reference's BLOCK_SIZE, constants.py:7) */
+  TMF_ERR_CUDA = -3               /* CUDA runtime / launch failure (message has the CUDA error string) */
+};
+
+/* `mode` of the fused kernels */
+enum {
+  TMF_MODE_FAITHFUL = 0, /* DCT -> full one-sided Jacobi SVD -> sigma0 += alpha*w -> U S' V^T -> IDCT,
+                            colour math bit-exact with the reference's float64 dot */
+  TMF_MODE_FAST = 1      /* algebraically reduced: top singular triplet of the spatial block and a
+                            rank-1 update (orthonormal DCT preserves singular values); fp32 colour */
+};
+
+int tmf_version(void);
+const char* tmf_last_error(void);
+
+/* Number of CUDA devices visible, or a negative error. */
+int tmf_device_count(void);
+
+/* embed_watermark on a batch.  rgb/out: n images of h x w x 3 bytes (out may not
+ * alias rgb).  wm: watermark map(s), (h/8) x (w/8) bytes each, already resized
+ * (resize_watermark stays on the host, watermarking.py:86-132); one map per
+ * image, or a single shared map when wm_shared != 0.  Pixels outside whole
+ * blocks (h%8, w%8 strips) take the colour round trip only, as in the
+ * reference.  alpha is double because the reference adds alpha*w in float64
+ * (watermarking.py:198). */
+int tmf_embed_rgb8(const uint8_t* rgb, uint8_t* out, int n, int h, int w, size_t img_stride,
+                   const uint8_t* wm, int wm_shared, double alpha, int block, int mode, void* stream);
+
+/* extract_watermark on a batch.  out_wm: n maps of (h/8) x (w/8) bytes. */
+int tmf_extract_rgb8(const uint8_t* wmk_rgb, const uint8_t* orig_rgb, uint8_t* out_wm, int n, int h, int w,
+                     size_t img_stride, double alpha, int block, int mode, void* stream);
+
+/* Tap: largest singular value of every whole luma block, float32, n x (h/8) x (w/8). */
+int tmf_sigma0_rgb8(const uint8_t* rgb, float* sigma0, int n, int h, int w, size_t img_stride, int block,
+                    int mode, void* stream);
+
+/* Batched SVD of nblocks row-major 8x8 float32 matrices (one-sided Jacobi).
+ * S: nblocks x 8, descending.  U, Vt: nblocks x 64 row-major, or both NULL for
+ * values only; A = U diag(S) Vt.  Columns of U whose singular value is below
+ * 1e-6*S[0] are completed to an orthonormal basis only if `complete_u` != 0
+ * (LAPACK's full_matrices=True contract); otherwise they are returned as zero
+ * columns (the reference only ever multiplies them by that singular value).
+ * sweeps (nullable): nblocks int32, Jacobi sweeps that rotated. */
+int tmf_svd8x8_f32(const float* blocks, int64_t nblocks, float* S, float* U, float* Vt, int32_t* sweeps,
+                   int complete_u, void* stream);
+
+/* Batched orthonormal 2-D DCT-II (inverse = 0) or its inverse (inverse = 1) of
+ * row-major 8x8 float32 blocks; in may equal out. */
+int tmf_dct8x8_f32(const float* in, float* out, int64_t nblocks, int inverse, void* stream);
+
+/* rgb_to_ycbcr / ycbcr_to_rgb taps on npixels interleaved pixels, bit-exact
+ * with the reference (float64 dot, float32 storage, truncating quantiser). */
+int tmf_rgb8_to_ycbcr_f32(const uint8_t* rgb, float* ycc, int64_t npixels, void* stream);
+int tmf_ycbcr_f32_to_rgb8(const float* ycc, uint8_t* rgb, int64_t npixels, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMF_WM_H */

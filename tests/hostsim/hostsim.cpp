@@ -1,0 +1,148 @@
+// CPU TEST HARNESS for the kernel arithmetic in thatsmyface_b200/csrc/tmf_math.cuh.
+// Built by tests/test_hostsim.py with g++ (-ffp-contract=off) so the per-block
+// math the CUDA kernels run can be checked against the oracle without a GPU.
+// It is test infrastructure: the product library (libtmfwm.so) never links or
+// calls it, and the product has no CPU path.
+#include <cstdint>
+#include <cstring>
+#include "../../thatsmyface_b200/csrc/tmf_math.cuh"
+#include "../../thatsmyface_b200/csrc/tmf_fast.cuh"
+
+using namespace tmf;
+
+static void load_luma(const uint8_t* rgb, int w, int by, int bx, float* a) {
+  for (int i = 0; i < 8; ++i)
+    for (int j = 0; j < 8; ++j) {
+      const uint8_t* p = rgb + ((size_t)(by * 8 + i) * w + bx * 8 + j) * 3;
+      a[8 * i + j] = luma_exact(unit_from_u8(p[0]), unit_from_u8(p[1]), unit_from_u8(p[2]));
+    }
+}
+
+extern "C" {
+
+int hostsim_embed(const uint8_t* rgb, uint8_t* out, int h, int w, const uint8_t* wm, double alpha,
+                  float* sigma_out, int* sweeps_out) {
+  const int nbh = h / 8, nbw = w / 8;
+  // colour round trip for every pixel first (strips keep this value)
+  for (size_t p = 0; p < (size_t)h * w; ++p) {
+    float r = unit_from_u8(rgb[3 * p]), g = unit_from_u8(rgb[3 * p + 1]), b = unit_from_u8(rgb[3 * p + 2]);
+    float cb, cr; chroma_exact(r, g, b, cb, cr);
+    uint32_t R, G, B; ycc_to_rgb8_exact(luma_exact(r, g, b), cb, cr, R, G, B);
+    out[3 * p] = (uint8_t)R; out[3 * p + 1] = (uint8_t)G; out[3 * p + 2] = (uint8_t)B;
+  }
+  for (int by = 0; by < nbh; ++by)
+    for (int bx = 0; bx < nbw; ++bx) {
+      float a[64], v[64];
+      load_luma(rgb, w, by, bx, a);
+      int sw;
+      float sig = embed_block_faithful(a, v, alpha, wm[by * nbw + bx], &sw);
+      if (sigma_out) sigma_out[by * nbw + bx] = sig;
+      if (sweeps_out) sweeps_out[by * nbw + bx] = sw;
+      for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 8; ++j) {
+          size_t p = (size_t)(by * 8 + i) * w + bx * 8 + j;
+          float r = unit_from_u8(rgb[3 * p]), g = unit_from_u8(rgb[3 * p + 1]), b = unit_from_u8(rgb[3 * p + 2]);
+          float cb, cr; chroma_exact(r, g, b, cb, cr);
+          uint32_t R, G, B; ycc_to_rgb8_exact(a[8 * i + j], cb, cr, R, G, B);
+          out[3 * p] = (uint8_t)R; out[3 * p + 1] = (uint8_t)G; out[3 * p + 2] = (uint8_t)B;
+        }
+    }
+  return 0;
+}
+
+int hostsim_extract(const uint8_t* wmk, const uint8_t* orig, uint8_t* out, int h, int w, double alpha) {
+  const int nbh = h / 8, nbw = w / 8;
+  for (int by = 0; by < nbh; ++by)
+    for (int bx = 0; bx < nbw; ++bx) {
+      float a[64];
+      load_luma(wmk, w, by, bx, a);
+      float sw = sigma0_block_faithful(a, nullptr);
+      load_luma(orig, w, by, bx, a);
+      float so = sigma0_block_faithful(a, nullptr);
+      out[by * nbw + bx] = (uint8_t)extract_level(sw, so, alpha);
+    }
+  return 0;
+}
+
+static void load_luma255(const uint8_t* rgb, int w, int by, int bx, float* a) {
+  for (int i = 0; i < 8; ++i)
+    for (int j = 0; j < 8; ++j) {
+      const uint8_t* p = rgb + ((size_t)(by * 8 + i) * w + bx * 8 + j) * 3;
+      a[8 * i + j] = luma255_fast((float)p[0], (float)p[1], (float)p[2]);
+    }
+}
+
+int hostsim_embed_fast(const uint8_t* rgb, uint8_t* out, int h, int w, const uint8_t* wm, double alpha,
+                       float* sigma_out, int* sweeps_out) {
+  const int nbh = h / 8, nbw = w / 8;
+  for (size_t p = 0; p < (size_t)h * w; ++p) {   // strips: exact colour round trip, as in the library
+    float r = unit_from_u8(rgb[3 * p]), g = unit_from_u8(rgb[3 * p + 1]), b = unit_from_u8(rgb[3 * p + 2]);
+    float cb, cr; chroma_exact(r, g, b, cb, cr);
+    uint32_t R, G, B; ycc_to_rgb8_exact(luma_exact(r, g, b), cb, cr, R, G, B);
+    out[3 * p] = (uint8_t)R; out[3 * p + 1] = (uint8_t)G; out[3 * p + 2] = (uint8_t)B;
+  }
+  for (int by = 0; by < nbh; ++by)
+    for (int bx = 0; bx < nbw; ++bx) {
+      float a[64];
+      load_luma255(rgb, w, by, bx, a);
+      int sq;
+      float sig = embed_block_fast(a, alpha, wm[by * nbw + bx], &sq);
+      if (sigma_out) sigma_out[by * nbw + bx] = sig;
+      if (sweeps_out) sweeps_out[by * nbw + bx] = sq;
+      for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 8; ++j) {
+          size_t p = (size_t)(by * 8 + i) * w + bx * 8 + j;
+          float R, G, B;
+          rgb255_out_fast((float)rgb[3 * p], (float)rgb[3 * p + 1], (float)rgb[3 * p + 2], a[8 * i + j], R, G, B);
+          out[3 * p] = (uint8_t)quant255(R); out[3 * p + 1] = (uint8_t)quant255(G); out[3 * p + 2] = (uint8_t)quant255(B);
+        }
+    }
+  return 0;
+}
+
+int hostsim_extract_fast(const uint8_t* wmk, const uint8_t* orig, uint8_t* out, int h, int w, double alpha) {
+  const int nbh = h / 8, nbw = w / 8;
+  for (int by = 0; by < nbh; ++by)
+    for (int bx = 0; bx < nbw; ++bx) {
+      float a[64];
+      load_luma255(wmk, w, by, bx, a);
+      float sw = sigma0_block_fast(a, nullptr);
+      load_luma255(orig, w, by, bx, a);
+      float so = sigma0_block_fast(a, nullptr);
+      out[by * nbw + bx] = (uint8_t)extract_level(sw, so, alpha);
+    }
+  return 0;
+}
+
+// full SVD of N row-major 8x8 blocks: S unsorted column norms, AV and V returned raw
+int hostsim_svd(const float* blocks, int64_t n, float* AV, float* V, float* S, int* sweeps) {
+  for (int64_t b = 0; b < n; ++b) {
+    float a[64], v[64], un;
+    std::memcpy(a, blocks + 64 * b, sizeof a);
+    sweeps[b] = jacobi_svd8<true>(a, v, un);
+    float n2[8]; column_norms2(a, n2);
+    for (int j = 0; j < 8; ++j) S[8 * b + j] = f_sqrt(n2[j]) * un;
+    for (int k = 0; k < 64; ++k) { AV[64 * b + k] = a[k] * un; V[64 * b + k] = v[k]; }
+  }
+  return 0;
+}
+
+int hostsim_dct(const float* in, float* out, int64_t n, int inverse) {
+  for (int64_t b = 0; b < n; ++b) {
+    float a[64];
+    std::memcpy(a, in + 64 * b, sizeof a);
+    if (inverse) idct8x8(a); else dct8x8(a);
+    std::memcpy(out + 64 * b, a, sizeof a);
+  }
+  return 0;
+}
+
+int hostsim_rgb2ycc(const uint8_t* rgb, float* ycc, int64_t npx) {
+  for (int64_t p = 0; p < npx; ++p) {
+    float r = unit_from_u8(rgb[3 * p]), g = unit_from_u8(rgb[3 * p + 1]), b = unit_from_u8(rgb[3 * p + 2]);
+    ycc[3 * p] = luma_exact(r, g, b);
+    chroma_exact(r, g, b, ycc[3 * p + 1], ycc[3 * p + 2]);
+  }
+  return 0;
+}
+}

@@ -1,0 +1,73 @@
+"""ctypes wrapper over tests/hostsim/_hostsim.so - the kernel arithmetic of
+thatsmyface_b200/csrc/tmf_math.cuh compiled for the host (TEST HARNESS ONLY)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
+SO = os.path.join(HERE, "_hostsim.so")
+SRC = os.path.join(HERE, "hostsim.cpp")
+HDR = os.path.join(os.path.dirname(HERE), "..", "thatsmyface_b200", "csrc", "tmf_math.cuh")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        stale = (not os.path.exists(SO)) or any(os.path.getmtime(p) > os.path.getmtime(SO) for p in (SRC, HDR))
+        if stale:
+            subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", SRC, "-o", SO, "-lm"],
+                           check=True)
+        _lib = C.CDLL(SO)
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def embed(rgb, wm, alpha=0.1, mode=0):
+    rgb = np.ascontiguousarray(rgb)
+    wm = np.ascontiguousarray(wm)
+    h, w = rgb.shape[:2]
+    nb = max(1, (h // 8) * (w // 8))
+    out = np.empty_like(rgb)
+    sig = np.zeros(nb, np.float32)
+    sw = np.zeros(nb, np.int32)
+    fn = lib().hostsim_embed if mode == 0 else lib().hostsim_embed_fast
+    fn(_p(rgb), _p(out), h, w, _p(wm), C.c_double(alpha), _p(sig), _p(sw))
+    return out, sig[: (h // 8) * (w // 8)].reshape(h // 8, w // 8), sw
+
+
+def extract(a, b, alpha=0.1, mode=0):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    h, w = a.shape[:2]
+    out = np.zeros((h // 8, w // 8), np.uint8)
+    fn = lib().hostsim_extract if mode == 0 else lib().hostsim_extract_fast
+    fn(_p(a), _p(b), _p(out), h, w, C.c_double(alpha))
+    return out
+
+
+def svd(blocks):
+    blocks = np.ascontiguousarray(blocks, np.float32).reshape(-1, 8, 8)
+    n = len(blocks)
+    AV, V, S = np.empty_like(blocks), np.empty_like(blocks), np.empty((n, 8), np.float32)
+    sw = np.zeros(n, np.int32)
+    lib().hostsim_svd(_p(blocks), C.c_int64(n), _p(AV), _p(V), _p(S), _p(sw))
+    return AV, V, S, sw
+
+
+def dct(blocks, inverse=False):
+    blocks = np.ascontiguousarray(blocks, np.float32).reshape(-1, 8, 8)
+    out = np.empty_like(blocks)
+    lib().hostsim_dct(_p(blocks), _p(out), C.c_int64(len(blocks)), 1 if inverse else 0)
+    return out
+
+
+def rgb2ycc(rgb):
+    rgb = np.ascontiguousarray(rgb)
+    out = np.empty(rgb.shape, np.float32)
+    lib().hostsim_rgb2ycc(_p(rgb), _p(out), C.c_int64(rgb.shape[0] * rgb.shape[1]))
+    return out

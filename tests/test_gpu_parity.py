@@ -1,0 +1,392 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the
+committed golden vectors of the reference.  Runs on the B200 box (`-m gpu`).
+
+Stated tolerances (north_star / SURVEY.md 8(c)):
+  * watermarked pixels: max |gpu - ref| <= 1 LSB (the reference's quantiser
+    truncates, so a 1e-7 difference that straddles an integer moves one LSB);
+  * per-block singular values: |s_k^gpu - s_k^ref| <= 1e-5 * s_0^ref (fp32);
+  * extracted map: grey level within +-1, thresholded bit (>= 128) exact
+    wherever the reference's level is not itself within 1 of the threshold,
+    recovered watermark bits exact;
+  * colour taps: bit-exact.
+"""
+import io
+import os
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from conftest import golden_names
+from oracle import wm_oracle as O
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from thatsmyface_b200 import watermarking as W  # noqa: E402
+from thatsmyface_b200.constants import MODE_FAITHFUL, MODE_FAST  # noqa: E402
+
+MODES = [MODE_FAITHFUL, MODE_FAST]
+ARRAY_CASES = [n for n in golden_names() if not n.startswith("pil_")]
+SIGMA_RTOL = 1e-5
+
+
+def natural_like(h, w, seed):
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w].astype(np.float64)
+    base = 120 + 70 * np.sin(x / 97.0) * np.cos(y / 71.0)
+    img = base[..., None] + np.array([10.0, 0.0, -10.0]) + rng.normal(0, 8, (h, w, 3))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def regions(h, w, seed):
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    img[: h // 4] = 0
+    img[h // 4: h // 2, : w // 2] = 255
+    img[h // 4: h // 2, w // 2:] = 128
+    img[h // 2: 3 * h // 4] = (np.arange(w) * 255 // max(w - 1, 1)).astype(np.uint8)[None, :, None]
+    img[2, 3] = (200, 10, 10)
+    img[5, 6] = (10, 180, 30)
+    return img
+
+
+def gpu_embed(rgb, wm, alpha=0.1, mode=MODE_FAITHFUL):
+    out = W.embed_tensor(torch.from_numpy(np.ascontiguousarray(rgb)).cuda(),
+                         torch.from_numpy(np.ascontiguousarray(wm)).cuda(), alpha, 8, mode)
+    return out.cpu().numpy()
+
+
+def gpu_extract(a, b, alpha=0.1, mode=MODE_FAITHFUL):
+    out = W.extract_tensor(torch.from_numpy(np.ascontiguousarray(a)).cuda(),
+                           torch.from_numpy(np.ascontiguousarray(b)).cuda(), alpha, 8, mode)
+    return out.cpu().numpy()
+
+
+def tie_mask(ref_S, rel=1e-4):
+    """Blocks whose two largest singular values are (nearly) tied: u0 v0^T is
+    ill-conditioned in the reference itself."""
+    s0, s1 = ref_S[..., 0], ref_S[..., 1]
+    return (s0 - s1) <= rel * np.maximum(s0, 1e-30)
+
+
+def assert_pixels(got, ref, ref_S=None, what=""):
+    d = np.abs(got.astype(int) - ref.astype(int))
+    if ref_S is not None and ref_S.size:
+        bad = np.repeat(np.repeat(tie_mask(ref_S), 8, 0), 8, 1)
+        full = np.zeros(d.shape[:2], bool)
+        full[: bad.shape[0], : bad.shape[1]] = bad
+        # an all-zero block is a tie (0 == 0) but fully defined by LAPACK's U = V = I
+        zero = np.repeat(np.repeat(ref_S[..., 0] == 0, 8, 0), 8, 1)
+        full[: zero.shape[0], : zero.shape[1]] &= ~zero
+        d = np.where(full[..., None], 0, d)
+    assert d.max() <= 1, f"{what}: max pixel difference {d.max()} LSB"
+    return float((d > 0).mean())
+
+
+def assert_extract(got, ref, what=""):
+    d = np.abs(got.astype(int) - ref.astype(int))
+    assert d.max() <= 1, f"{what}: extracted level differs by {d.max()}"
+    decided = np.abs(ref.astype(int) - 128) > 1
+    assert np.array_equal((got >= 128)[decided], (ref >= 128)[decided]), f"{what}: thresholded bits differ"
+
+
+# --------------------------------------------------------------------------- taps
+@pytest.mark.parametrize("name", ARRAY_CASES)
+def test_rgb_to_ycbcr_bit_exact(golden, name):
+    g = golden(name)
+    assert np.array_equal(W.rgb_to_ycbcr(g["rgb"]), g["ref_ycc"])
+    assert np.array_equal(W.rgb_to_ycbcr(Image.fromarray(g["rgb"])), g["ref_ycc"])
+
+
+def test_rgb_to_ycbcr_bit_exact_dense_sample():
+    rng = np.random.default_rng(17)
+    rgb = rng.integers(0, 256, (512, 1024, 3), dtype=np.uint8)
+    rgb[0, :256] = np.arange(256, dtype=np.uint8)[:, None]   # all greys
+    assert np.array_equal(W.rgb_to_ycbcr(rgb), O.rgb_to_ycbcr(rgb))
+
+
+def test_rgba_input_drops_alpha():
+    rng = np.random.default_rng(2)
+    rgba = rng.integers(0, 256, (16, 24, 4), dtype=np.uint8)
+    assert np.array_equal(W.rgb_to_ycbcr(rgba), O.rgb_to_ycbcr(rgba))
+
+
+def test_ycbcr_to_rgb_bit_exact():
+    rng = np.random.default_rng(3)
+    ycc = (rng.random((300, 400, 3), dtype=np.float32) * np.float32(1.3) - np.float32(0.15))
+    assert np.array_equal(W.ycbcr_to_rgb(ycc), O.ycbcr_to_rgb(ycc))
+    g = O.rgb_to_ycbcr(rng.integers(0, 256, (64, 64, 3), dtype=np.uint8))
+    assert np.array_equal(W.ycbcr_to_rgb(g), O.ycbcr_to_rgb(g))
+
+
+def test_dct_taps_match_scipy():
+    rng = np.random.default_rng(4)
+    blocks = rng.random((1000, 8, 8), dtype=np.float32)
+    d = W.dct8x8(torch.from_numpy(blocks).cuda()).cpu().numpy()
+    ref = O.dct_blocks(blocks)
+    assert np.abs(d - ref).max() <= 2e-6
+    back = W.dct8x8(torch.from_numpy(ref).cuda(), inverse=True).cpu().numpy()
+    assert np.abs(back - blocks).max() <= 2e-6
+    one = W.apply_dct_to_block(blocks[0])
+    assert one.shape == (8, 8) and np.abs(one - O.apply_dct_to_block(blocks[0])).max() <= 2e-6
+    assert np.abs(W.apply_idct_to_block(one) - blocks[0]).max() <= 2e-6
+
+
+def _dct_luma_blocks(rgb):
+    Y = O.rgb_to_ycbcr(rgb)[:, :, 0]
+    return O.dct_blocks(O.to_blocks(Y)).reshape(-1, 8, 8)
+
+
+@pytest.mark.parametrize("kind", ["random", "natural", "regions", "scaled"])
+def test_svd_singular_values_and_factors(kind):
+    rng = np.random.default_rng(5)
+    if kind == "random":
+        D = _dct_luma_blocks(rng.integers(0, 256, (256, 256, 3), dtype=np.uint8))
+    elif kind == "natural":
+        D = _dct_luma_blocks(natural_like(256, 256, 1))
+    elif kind == "regions":
+        D = _dct_luma_blocks(regions(256, 256, 2))
+    else:  # magnitudes far from 1: exercises the power-of-two pre-scaling
+        D = (rng.normal(size=(512, 8, 8)) * 10.0 ** rng.integers(-12, 12, (512, 1, 1))).astype(np.float32)
+    (U, S, Vt), sweeps = W.svd8x8(torch.from_numpy(D).cuda(), vectors=True, return_sweeps=True)
+    U, S, Vt, sweeps = U.cpu().numpy(), S.cpu().numpy(), Vt.cpu().numpy(), sweeps.cpu().numpy()
+    Sref = np.linalg.svd(D.astype(np.float64), compute_uv=False)
+    S32 = np.linalg.svd(D, compute_uv=False)           # what the reference computes (sgesdd)
+    s0 = np.maximum(Sref[:, :1], 1e-300)
+    assert (np.diff(S, axis=1) <= 0).all(), "singular values must be descending"
+    assert (np.abs(S - S32) <= SIGMA_RTOL * s0).all()
+    assert (np.abs(S - Sref) <= SIGMA_RTOL * s0).all()
+    # A = U diag(S) Vt
+    rec = np.einsum("nik,nk,nkj->nij", U, S, Vt)
+    assert (np.abs(rec - D).reshape(len(D), -1).max(1) <= 2e-6 * s0[:, 0] + 1e-37).all()
+    # V orthogonal
+    assert np.abs(np.einsum("nik,njk->nij", Vt, Vt) - np.eye(8)).max() <= 5e-6
+    # top triplet, sign-invariant, on well separated blocks
+    Ur, Sr, Vtr = np.linalg.svd(D.astype(np.float64))
+    sep = (Sr[:, 0] - Sr[:, 1]) > 1e-2 * Sr[:, 0]
+    p_gpu = np.einsum("ni,nj->nij", U[:, :, 0], Vt[:, 0, :])
+    p_ref = np.einsum("ni,nj->nij", Ur[:, :, 0], Vtr[:, 0, :])
+    assert np.abs(p_gpu - p_ref)[sep].max() <= 2e-5
+    assert sweeps.max() <= 12 and sweeps.min() >= 0
+    # values-only entry point agrees
+    S2 = W.svd8x8(torch.from_numpy(D).cuda(), vectors=False).cpu().numpy()
+    assert (np.abs(S2 - S32) <= SIGMA_RTOL * s0).all()
+
+
+def test_svd_complete_u_gives_orthogonal_factor():
+    D = _dct_luma_blocks(regions(128, 128, 3))          # many rank-deficient blocks
+    U, S, Vt = (t.cpu().numpy() for t in W.svd8x8(torch.from_numpy(D).cuda(), vectors=True, complete_u=True))
+    assert np.abs(np.einsum("nki,nkj->nij", U, U) - np.eye(8)).max() <= 1e-5
+    rec = np.einsum("nik,nk,nkj->nij", U, S, Vt)
+    assert np.abs(rec - D).max() <= 1e-5
+
+
+def test_svd_degenerate_inputs():
+    D = np.zeros((4, 8, 8), np.float32)
+    D[1] = 0.5                                          # constant block: rank 1
+    D[2, 0, 0] = 3.0
+    D[3] = np.eye(8) * 2                                # fully tied
+    U, S, Vt = (t.cpu().numpy() for t in W.svd8x8(torch.from_numpy(D).cuda()))
+    assert np.isfinite(U).all() and np.isfinite(S).all() and np.isfinite(Vt).all()
+    assert np.allclose(S[0], 0) and np.allclose(S[1], [4.0] + [0] * 7, atol=1e-6)
+    assert np.allclose(S[2], [3.0] + [0] * 7) and np.allclose(S[3], 2.0)
+
+
+def test_sigma0_tap_matches_reference_singular_values(golden):
+    g = golden("gv1_random64")
+    s0 = W.sigma0_tensor(torch.from_numpy(g["rgb"]).cuda()).cpu().numpy()
+    ref = g["ref_S"][..., 0]
+    assert (np.abs(s0 - ref) <= SIGMA_RTOL * ref).all()
+
+
+# --------------------------------------------------------------------------- golden vectors of the reference
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", ARRAY_CASES)
+def test_embed_extract_against_reference_vectors(golden, name, mode):
+    g = golden(name)
+    out = gpu_embed(g["rgb"], g["wm"], mode=mode)
+    assert out.shape == g["ref_out"].shape and out.dtype == np.uint8
+    assert_pixels(out, g["ref_out"], g.get("ref_S"), f"{name} mode {mode}")
+    if g["wm"].size:
+        ext = gpu_extract(g["ref_out"], g["rgb"], mode=mode)
+        assert_extract(ext, g["ref_ext"], f"{name} mode {mode}")
+        # cross: the reference's extractor reads the GPU's embedding like its own
+        cross = O.extract_array(out, g["rgb"])
+        assert np.abs(cross.astype(int) - g["ref_ext"].astype(int)).max() <= 2
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_flat_kats(golden, mode):
+    """SURVEY.md 8(c) KAT-flat: degenerate blocks (sigma0 = 0 / rank 1 / saturated)."""
+    for name, pix, lvl in (("flat_black16", 3, 239), ("flat_gray16", 131, 239), ("flat_white16", 255, 0)):
+        g = golden(name)
+        out = gpu_embed(g["rgb"], g["wm"], mode=mode)
+        assert np.abs(out.astype(int) - pix).max() <= 1, name
+        ext = gpu_extract(g["ref_out"], g["rgb"], mode=mode)
+        assert np.abs(ext.astype(int) - lvl).max() <= 1, name
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", ["pil_png_preserve1", "pil_png_preserve0"])
+def test_pil_api_drop_in(golden, name, mode):
+    g = golden(name)
+    pr = name.endswith("1")
+    s = {"block_size": 8, "alpha": 0.1, "mode": mode}
+    img = Image.fromarray(g["rgb"])
+    out = W.embed_watermark(img, g["png"].tobytes(), pr, s)
+    assert isinstance(out, Image.Image) and out.mode == "RGB" and out.size == img.size
+    assert_pixels(np.array(out), g["ref_out"], what=name)
+    out2 = W.embed_watermark(img.convert("RGBA"), Image.open(io.BytesIO(g["png"].tobytes())), pr, s)
+    assert np.array_equal(np.array(out2), np.array(out))
+    ext = W.extract_watermark(Image.fromarray(g["ref_out"]), img, s)
+    assert ext.mode == "L" and ext.size == (25, 16)
+    assert_extract(np.array(ext), g["ref_ext"], name)
+
+
+# --------------------------------------------------------------------------- seeded inputs vs the oracle
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("kind,shape", [("random", (256, 384)), ("natural", (264, 328)), ("regions", (256, 256)),
+                                        ("gray", (128, 136)), ("natural", (203, 187)), ("natural", (100, 100))])
+def test_embed_extract_vs_oracle(kind, shape, mode):
+    h, w = shape
+    rng = np.random.default_rng(h * 1000 + w)
+    if kind == "random":
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    elif kind == "natural":
+        rgb = natural_like(h, w, 7)
+    elif kind == "regions":
+        rgb = regions(h, w, 8)
+    else:
+        rgb = np.repeat(natural_like(h, w, 9)[:, :, 1:2], 3, axis=2)
+    wm = np.where(rng.random((h // 8, w // 8)) < 0.5, 0, 255).astype(np.uint8)
+    wm[0, :] = rng.integers(0, 256, w // 8)      # some grey levels too
+    taps = {}
+    ref = O.embed_array(rgb, wm, taps=taps)
+    out = gpu_embed(rgb, wm, mode=mode)
+    frac = assert_pixels(out, ref, taps["S"], f"{kind}{shape} mode {mode}")
+    if kind in ("random", "natural"):
+        assert frac <= 2e-3, f"{frac:.2e} of samples differ"     # expected ~1e-4 .. 4e-4
+    assert_extract(gpu_extract(ref, rgb, mode=mode), O.extract_array(ref, rgb), f"{kind}{shape}")
+    # GPU end to end: the bits that went in come out
+    ext = gpu_extract(out, rgb, mode=mode)
+    sat = O.to_blocks(O.rgb_to_ycbcr(rgb)[:, :, 0]).max(axis=(2, 3)) > 0.9   # blocks that clip at white
+    ok = ~sat[: wm.shape[0], : wm.shape[1]]
+    ok[0, :] = False
+    assert np.array_equal((ext >= 128)[ok], (wm >= 128)[ok])
+
+
+@pytest.mark.parametrize("alpha", [0.1, 0.5, 1.0])
+def test_alpha_range_of_the_ui(alpha):
+    rgb = natural_like(64, 96, 12)
+    rng = np.random.default_rng(1)
+    wm = rng.integers(0, 256, (8, 12), dtype=np.uint8)
+    taps = {}
+    ref = O.embed_array(rgb, wm, alpha, taps=taps)
+    for mode in MODES:
+        assert_pixels(gpu_embed(rgb, wm, alpha, mode), ref, taps["S"], f"alpha {alpha}")
+        assert_extract(gpu_extract(ref, rgb, alpha, mode), O.extract_array(ref, rgb, alpha), f"alpha {alpha}")
+
+
+def test_batch_with_per_image_and_shared_maps():
+    rng = np.random.default_rng(21)
+    imgs = np.stack([natural_like(48, 64, s) for s in range(5)])
+    wms = rng.integers(0, 256, (5, 6, 8), dtype=np.uint8)
+    x = torch.from_numpy(imgs).cuda()
+    for mode in MODES:
+        per = W.embed_tensor(x, torch.from_numpy(wms).cuda(), mode=mode).cpu().numpy()
+        shared = W.embed_tensor(x, torch.from_numpy(wms[0]).cuda(), mode=mode).cpu().numpy()
+        for k in range(5):
+            assert_pixels(per[k], O.embed_array(imgs[k], wms[k]), what=f"per-image {k}")
+            assert_pixels(shared[k], O.embed_array(imgs[k], wms[0]), what=f"shared {k}")
+        ext = W.extract_tensor(torch.from_numpy(per).cuda(), x, mode=mode).cpu().numpy()
+        for k in range(5):
+            assert_extract(ext[k], O.extract_array(per[k], imgs[k]), f"extract {k}")
+
+
+def test_unaligned_device_pointers_take_the_narrow_path():
+    """Tensor views whose base address is not 8-byte aligned (VEC=4/1 kernels)."""
+    rgb = natural_like(40, 52, 5)           # 3*52 = 156: 4-byte rows
+    wm = np.full((5, 6), 255, np.uint8)
+    ref = O.embed_array(rgb, wm)
+    assert_pixels(gpu_embed(rgb, wm), ref)
+    rgb = natural_like(40, 51, 5)           # 3*51 = 153: byte path
+    wm = np.full((5, 6), 255, np.uint8)
+    assert_pixels(gpu_embed(rgb, wm), O.embed_array(rgb, wm))
+    assert_extract(gpu_extract(O.embed_array(rgb, wm), rgb), O.extract_array(O.embed_array(rgb, wm), rgb))
+
+
+def test_empty_and_sub_block_inputs():
+    x = torch.zeros((0, 16, 16, 3), dtype=torch.uint8, device="cuda")
+    assert W.embed_tensor(x, torch.zeros((2, 2), dtype=torch.uint8, device="cuda")).shape == (0, 16, 16, 3)
+    rng = np.random.default_rng(3)
+    rgb = rng.integers(0, 256, (5, 7, 3), dtype=np.uint8)      # no whole block: colour round trip only
+    out = gpu_embed(rgb, np.zeros((0, 0), np.uint8))
+    assert np.array_equal(out, O.ycbcr_to_rgb(O.rgb_to_ycbcr(rgb)))
+    assert gpu_extract(rgb, rgb).shape == (0, 0)
+
+
+def test_errors_are_loud_and_typed():
+    x = torch.zeros((16, 16, 3), dtype=torch.uint8, device="cuda")
+    m = torch.zeros((2, 2), dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError, match="block_size 4 is not supported"):
+        W.embed_tensor(x, m, block_size=4)
+    with pytest.raises(ValueError, match="block_size"):
+        W.embed_watermark(Image.new("RGB", (16, 16)), Image.new("L", (2, 2)), False, {"block_size": 16, "alpha": 0.1})
+    with pytest.raises(ValueError, match="watermark map"):
+        W.embed_tensor(x, torch.zeros((3, 2), dtype=torch.uint8, device="cuda"))
+    with pytest.raises(ValueError, match="same shape"):
+        W.extract_tensor(x, torch.zeros((24, 16, 3), dtype=torch.uint8, device="cuda"))
+    with pytest.raises(ValueError, match="same size"):
+        W.extract_watermark(Image.new("RGB", (16, 16)), Image.new("RGB", (24, 16)))
+    with pytest.raises(ValueError):
+        W.embed_tensor(x.float(), m)
+
+
+# --------------------------------------------------------------------------- full-size properties (no oracle at this size)
+@pytest.mark.parametrize("mode", MODES)
+def test_1080p_batch_round_trip_and_shard_invariance(mode):
+    n, h, w = 6, 1080, 1920
+    g = torch.Generator(device="cuda").manual_seed(0)
+    yy = torch.arange(h, device="cuda").view(1, h, 1, 1)
+    xx = torch.arange(w, device="cuda").view(1, 1, w, 1)
+    base = 120 + 70 * torch.sin(xx / 97.0) * torch.cos(yy / 71.0)
+    imgs = (base + torch.randn((n, h, w, 3), device="cuda", generator=g) * 8).clamp(0, 255).to(torch.uint8)
+    wm = (torch.rand((135, 240), device="cuda", generator=g) < 0.5).to(torch.uint8) * 255
+    out = W.embed_tensor(imgs, wm, mode=mode)
+    ext = W.extract_tensor(out, imgs, mode=mode)
+    assert torch.equal(ext >= 128, (wm >= 128).expand(n, -1, -1)), "watermark bits must survive embed -> extract"
+    # idempotence of the zero mark: extract(x, x) is all zero
+    assert int(W.extract_tensor(imgs, imgs, mode=mode).max()) == 0
+    # embedding image k alone equals slice k of the batch (sharding by image changes nothing)
+    alone = W.embed_tensor(imgs[3:5], wm, mode=mode)
+    assert torch.equal(alone, out[3:5])
+    # change is confined: |out - in| small, and one image against the oracle
+    assert int((out.int() - imgs.int()).abs().max()) <= 12
+    ref = O.embed_array(imgs[0].cpu().numpy(), wm.cpu().numpy())
+    assert_pixels(out[0].cpu().numpy(), ref, what="1080p image 0")
+
+
+def test_host_pipeline_matches_device_path():
+    rng = np.random.default_rng(8)
+    imgs = np.stack([natural_like(72, 96, s) for s in range(7)])
+    wm = rng.integers(0, 256, (9, 12), dtype=np.uint8)
+    direct = W.embed_tensor(torch.from_numpy(imgs).cuda(), torch.from_numpy(wm).cuda()).cpu().numpy()
+    from thatsmyface_b200.pipeline import run_batch
+    stats = {}
+    piped = run_batch("embed", imgs, None, wm, chunk_bytes=3 * 72 * 96 * 3, stats=stats)
+    assert isinstance(piped, np.ndarray) and np.array_equal(piped, direct)
+    assert stats["launches"] == 3 and stats["h2d_bytes"] == imgs.size and stats["d2h_bytes"] == imgs.size
+    pinned = torch.from_numpy(imgs).pin_memory()
+    piped_t = W.embed_watermark_batch(pinned, wm)
+    assert isinstance(piped_t, torch.Tensor) and piped_t.is_pinned() and np.array_equal(piped_t.numpy(), direct)
+    wms = rng.integers(0, 256, (7, 9, 12), dtype=np.uint8)
+    per = W.embed_watermark_batch(imgs, wms)
+    want = W.embed_tensor(torch.from_numpy(imgs).cuda(), torch.from_numpy(wms).cuda()).cpu().numpy()
+    assert np.array_equal(per, want)
+    ext = W.extract_watermark_batch(per, imgs)
+    want_e = W.extract_tensor(torch.from_numpy(per).cuda(), torch.from_numpy(imgs).cuda()).cpu().numpy()
+    assert np.array_equal(ext, want_e)
+    if torch.cuda.device_count() > 1:
+        two = W.embed_watermark_batch(imgs, wm, devices=[0, 1])
+        assert np.array_equal(two, direct)

@@ -1,0 +1,132 @@
+"""CPU-side checks: the C-ABI library loads and exports what include/tmf_wm.h
+declares, the host shim mirrors the reference's settings / resize / error
+behaviour, and nothing computes without a GPU (no CPU fallback)."""
+import io
+import os
+import re
+import sys
+import types
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from conftest import ROOT
+from oracle import wm_oracle as O
+from thatsmyface_b200 import _lib, build as tmf_build
+from thatsmyface_b200 import watermarking as W
+from thatsmyface_b200.pipeline import shard_ranges
+
+torch = pytest.importorskip("torch")
+NO_GPU = not torch.cuda.is_available()
+
+
+@pytest.fixture(scope="module")
+def lib():
+    tmf_build.build()          # no-op when the in-tree .so is current
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "tmf_wm.h")).read()
+    declared = set(re.findall(r"\b(tmf_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.tmf_version() == 100
+
+
+def test_argument_validation_happens_before_any_cuda_work(lib):
+    # these return from the host-side checks, so they are safe without a GPU
+    assert lib.tmf_embed_rgb8(None, None, 1, 16, 16, 16 * 16 * 3, None, 1, 0.1, 4, 0, None) == -2
+    assert "block_size 4 is not supported" in _lib.last_error()
+    assert lib.tmf_embed_rgb8(None, None, 1, 16, 16, 16 * 16 * 3, None, 1, 0.1, 8, 0, None) == -1
+    assert lib.tmf_embed_rgb8(None, None, 1, 16, 16, 10, None, 1, 0.1, 8, 0, None) == -1
+    assert "img_stride" in _lib.last_error()
+    assert lib.tmf_embed_rgb8(None, None, 1, 16, 16, 768, None, 1, 0.1, 8, 7, None) == -1
+    assert lib.tmf_extract_rgb8(None, None, None, 1, 16, 16, 768, 0.0, 8, 0, None) == -1
+    assert lib.tmf_svd8x8_f32(None, -1, None, None, None, None, 0, None) == -1
+    assert lib.tmf_svd8x8_f32(None, 0, None, None, None, None, 0, None) == 0
+    assert lib.tmf_embed_rgb8(None, None, 0, 16, 16, 768, None, 1, 0.1, 8, 0, None) == 0   # empty batch
+    with pytest.raises(ValueError):
+        _lib.check(-1)
+    with pytest.raises(RuntimeError):
+        _lib.check(-3)
+
+
+@pytest.mark.skipif(not NO_GPU, reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback():
+    img = Image.new("RGB", (16, 16))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        W.embed_watermark(img, Image.new("L", (2, 2)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        W.extract_watermark(img, img)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        W.rgb_to_ycbcr(img)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        W.embed_watermark_batch(np.zeros((1, 16, 16, 3), np.uint8), np.zeros((2, 2), np.uint8))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "thatsmyface_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle/make_golden.py", ""), f
+
+
+def test_settings_precedence(monkeypatch):
+    """explicit truthy dict -> st.session_state.custom_settings -> constants
+    (modules/watermarking.py:10-20, :149-151)."""
+    monkeypatch.delitem(sys.modules, "streamlit", raising=False)
+    assert W.get_watermark_settings() == {"block_size": 8, "alpha": 0.1}
+    assert W._resolve(None)[:2] == (8, 0.1)
+    assert W._resolve({})[:2] == (8, 0.1)                      # falsy dict falls through
+    assert W._resolve({"alpha": 0.5})[:2] == (8, 0.5)
+    st = types.ModuleType("streamlit")
+
+    class State(dict):
+        __getattr__ = dict.__getitem__
+
+    st.session_state = State()
+    monkeypatch.setitem(sys.modules, "streamlit", st)
+    assert W.get_watermark_settings() == {"block_size": 8, "alpha": 0.1}     # key absent
+    st.session_state["custom_settings"] = {"alpha": 0.3}
+    assert W.get_watermark_settings() == {"block_size": 8, "alpha": 0.3}
+    st.session_state["custom_settings"] = {"block_size": 16, "alpha": 1.0}
+    assert W._resolve(None)[:2] == (16, 1.0)
+    assert W._resolve({"block_size": 8})[:2] == (8, 0.1)       # explicit dict wins, missing keys -> constants
+    st.session_state["custom_settings"] = {}                   # the embed page's initial value
+    assert W.get_watermark_settings() == {"block_size": 8, "alpha": 0.1}
+
+
+@pytest.mark.parametrize("name", ["pil_png_preserve1", "pil_png_preserve0"])
+def test_resize_watermark_matches_reference(golden, name):
+    g = golden(name)
+    pr = name.endswith("1")
+    png = g["png"].tobytes()
+    got = W.resize_watermark(png, 16, 25, pr)
+    assert got.mode == "L" and got.size == (25, 16)
+    assert np.array_equal(np.array(got), g["wm"])
+    got2 = W.resize_watermark(Image.open(io.BytesIO(png)).convert("RGB"), 16, 25, pr)
+    assert np.array_equal(np.array(got2), g["wm"])
+    assert np.array_equal(np.array(got), np.array(O.resize_watermark(png, 16, 25, pr)))
+
+
+def test_resize_watermark_shapes():
+    wide = Image.fromarray(np.zeros((10, 40), np.uint8))
+    out = np.array(W.resize_watermark(wide, 20, 20, True))
+    assert out.shape == (20, 20) and (out[:7] == 255).all() and (out[-7:] == 255).all() and (out[8:12] == 0).all()
+    same = Image.fromarray(np.arange(12, dtype=np.uint8).reshape(3, 4))
+    assert np.array_equal(np.array(W.resize_watermark(same, 3, 4, False)), np.array(same))
+
+
+def test_shard_ranges_partition_by_image():
+    for n in (0, 1, 7, 8, 1024, 1000):
+        for parts in (1, 2, 4, 8):
+            r = shard_ranges(n, parts)
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            sizes = [e - s for s, e in r]
+            assert max(sizes) - min(sizes) <= 1

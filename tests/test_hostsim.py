@@ -1,0 +1,100 @@
+"""The kernels' per-block arithmetic (thatsmyface_b200/csrc/tmf_math.cuh and
+tmf_fast.cuh compiled for the host by tests/hostsim) against the oracle.  This
+is how the CUDA math is checked in the build container, which has no GPU; the
+`-m gpu` suite repeats the same checks through the real library."""
+import numpy as np
+import pytest
+
+import hostsim_util as H
+from conftest import golden_names
+from oracle import wm_oracle as O
+from oracle.make_golden import natural_like, regions
+
+ARRAY_CASES = [n for n in golden_names() if not n.startswith("pil_") and n != "subblock_5x7"]
+
+
+def _tie(S, rel=1e-4):
+    s0, s1 = S[..., 0], S[..., 1]
+    return ((s0 - s1) <= rel * np.maximum(s0, 1e-30)) & (s0 > 0)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("name", ARRAY_CASES)
+def test_embed_extract_math_vs_reference_vectors(golden, name, mode):
+    g = golden(name)
+    out, sig, _ = H.embed(g["rgb"], g["wm"], mode=mode)
+    d = np.abs(out.astype(int) - g["ref_out"].astype(int))
+    bad = np.repeat(np.repeat(_tie(g["ref_S"]), 8, 0), 8, 1)
+    d[: bad.shape[0], : bad.shape[1]][bad] = 0
+    assert d.max() <= 1
+    s0 = g["ref_S"][..., 0]
+    assert (np.abs(sig - s0) <= 1e-5 * s0 + 1e-12).all()
+    ext = H.extract(g["ref_out"], g["rgb"], mode=mode)
+    de = np.abs(ext.astype(int) - g["ref_ext"].astype(int))
+    assert de.max() <= 1
+    decided = np.abs(g["ref_ext"].astype(int) - 128) > 1
+    assert np.array_equal((ext >= 128)[decided], (g["ref_ext"] >= 128)[decided])
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("kind", ["random", "natural", "regions", "gray"])
+def test_embed_extract_math_vs_oracle(kind, mode):
+    rng = np.random.default_rng(5)
+    img = {"random": lambda: rng.integers(0, 256, (128, 160, 3), dtype=np.uint8),
+           "natural": lambda: natural_like(136, 200, 2),
+           "regions": lambda: regions(128, 128, 4),
+           "gray": lambda: np.repeat(natural_like(64, 64, 9)[:, :, 1:2], 3, 2)}[kind]()
+    h, w = img.shape[:2]
+    wm = (rng.integers(0, 2, (h // 8, w // 8)) * 255).astype(np.uint8)
+    wm[0] = rng.integers(0, 256, w // 8)
+    taps = {}
+    ref = O.embed_array(img, wm, taps=taps)
+    out, sig, iters = H.embed(img, wm, mode=mode)
+    d = np.abs(out.astype(int) - ref.astype(int))
+    bad = np.repeat(np.repeat(_tie(taps["S"]), 8, 0), 8, 1)
+    d[bad] = 0
+    assert d.max() <= 1
+    if kind in ("random", "natural"):
+        assert (d > 0).mean() <= 2e-3
+    assert iters.max() <= (12 if mode == 0 else 18)
+    rext = O.extract_array(ref, img)
+    ext = H.extract(ref, img, mode=mode)
+    assert np.abs(ext.astype(int) - rext.astype(int)).max() <= 1
+    # own round trip recovers the bits wherever the block does not clip at white
+    ext2 = H.extract(out, img, mode=mode)
+    ok = O.to_blocks(O.rgb_to_ycbcr(img)[:, :, 0]).max(axis=(2, 3)) <= 0.9
+    ok[0] = False
+    assert np.array_equal((ext2 >= 128)[ok], (wm >= 128)[ok])
+
+
+@pytest.mark.parametrize("alpha", [0.5, 1.0])
+def test_alpha_range(alpha):
+    img = natural_like(64, 96, 12)
+    wm = np.random.default_rng(1).integers(0, 256, (8, 12), dtype=np.uint8)
+    ref = O.embed_array(img, wm, alpha)
+    for mode in (0, 1):
+        out, _, _ = H.embed(img, wm, alpha, mode)
+        assert np.abs(out.astype(int) - ref.astype(int)).max() <= 1
+        assert np.abs(H.extract(ref, img, alpha, mode).astype(int) - O.extract_array(ref, img, alpha).astype(int)).max() <= 1
+
+
+def test_jacobi_svd_math():
+    rng = np.random.default_rng(7)
+    D = O.dct_blocks(O.to_blocks(O.rgb_to_ycbcr(regions(128, 128, 2))[:, :, 0])).reshape(-1, 8, 8)
+    D = np.concatenate([D, (rng.normal(size=(256, 8, 8)) * 10.0 ** rng.integers(-12, 12, (256, 1, 1))).astype(np.float32)])
+    AV, V, S, sweeps = H.svd(D)
+    Sref = np.linalg.svd(D.astype(np.float64), compute_uv=False)
+    s0 = np.maximum(Sref[:, :1], 1e-300)
+    assert (np.abs(-np.sort(-S, axis=1) - Sref) <= 1e-5 * s0).all()
+    assert np.abs(np.einsum("nki,nkj->nij", V, V) - np.eye(8)).max() <= 5e-6
+    assert (np.abs(np.einsum("nik,njk->nij", AV, V) - D).reshape(len(D), -1).max(1) <= 2e-6 * s0[:, 0]).all()
+    assert sweeps.max() <= 10
+
+
+def test_dct_and_colour_math():
+    rng = np.random.default_rng(8)
+    b = rng.random((500, 8, 8), dtype=np.float32)
+    assert np.abs(H.dct(b) - O.dct_blocks(b)).max() <= 2e-6
+    assert np.abs(H.dct(O.dct_blocks(b), inverse=True) - b).max() <= 2e-6
+    rgb = rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)
+    assert np.array_equal(H.rgb2ycc(rgb), O.rgb_to_ycbcr(rgb))

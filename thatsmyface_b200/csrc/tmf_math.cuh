@@ -1,0 +1,418 @@
+// Per-block arithmetic of the DCT+SVD watermark path, written so that one
+// thread owns one 8x8 block entirely in registers (every array index below is
+// a compile-time constant after unrolling).
+//
+// Reference semantics (Rigelyon/ThatsMyFace, modules/watermarking.py):
+//   colour in   :23-50    colour out :53-73    DCT :76-78    IDCT :81-83
+//   SVD         :195, :279-282 (numpy.linalg.svd -> LAPACK sgesdd)
+//   modulation  :198      inverse SVD :201     extract epilogue :285-289
+//
+// The functions are __host__ __device__ so the same source can be compiled for
+// the host by tests/hostsim (a CPU *test harness* for the kernel arithmetic;
+// the product library never takes that path).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define TMF_HD __host__ __device__ __forceinline__
+#else
+#define TMF_HD inline
+#endif
+
+namespace tmf {
+
+// ---------------------------------------------------------------------------
+// rounding-explicit primitives (device intrinsics; plain C on the host, where
+// the test harness is built with -ffp-contract=off)
+// ---------------------------------------------------------------------------
+TMF_HD float f_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fdiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
+TMF_HD float f_add(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  volatile float r = a + b; return r;
+#endif
+}
+TMF_HD float f_mul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  volatile float r = a * b; return r;
+#endif
+}
+TMF_HD double d_mul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b);
+#else
+  volatile double r = a * b; return r;
+#endif
+}
+TMF_HD double d_div(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __ddiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
+TMF_HD float f_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  return __fsqrt_rn(x);
+#else
+  return sqrtf(x);
+#endif
+}
+TMF_HD double d_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rn(a, b, c);
+#else
+  return fma(a, b, c);
+#endif
+}
+TMF_HD float f_rsqrt(float x) {   // 1/sqrt(x), a few ulp; refined by the caller where it matters
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+TMF_HD float f_sqrt_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return sqrtf(x);
+#endif
+}
+TMF_HD float f_rcp_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return 1.0f / x;
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// colour transforms, bit-exact with the reference
+//
+// The reference computes np.dot(T64, x32) per pixel: float32 pixel promoted to
+// float64, OpenBLAS dgemv accumulating fma(T[r][2],x2, fma(T[r][0],x0, T[r][1]*x1))
+// (order pinned exhaustively over all 2^24 RGB triplets by oracle/make_golden.py),
+// and the float64 result rounded to float32 on store.
+// ---------------------------------------------------------------------------
+TMF_HD float dot3_npdot(double t0, double t1, double t2, float x0, float x1, float x2) {
+  double acc = d_mul(t1, (double)x1);
+  acc = d_fma(t0, (double)x0, acc);
+  acc = d_fma(t2, (double)x2, acc);
+  return (float)acc;
+}
+
+// watermarking.py:29 - f32(u8) / 255.0 (IEEE float32 division)
+TMF_HD float unit_from_u8(uint32_t v) { return f_div((float)v, 255.0f); }
+
+// watermarking.py:37-48 (Y only)
+TMF_HD float luma_exact(float r, float g, float b) {
+  return dot3_npdot(0.299, 0.587, 0.114, r, g, b);
+}
+// watermarking.py:37-48 (Cb, Cr with the float32 "+= 0.5" of :48)
+TMF_HD void chroma_exact(float r, float g, float b, float& cb, float& cr) {
+  cb = f_add(dot3_npdot(-0.169, -0.331, 0.5, r, g, b), 0.5f);
+  cr = f_add(dot3_npdot(0.5, -0.419, -0.081, r, g, b), 0.5f);
+}
+// watermarking.py:58-73: "-= 0.5" in float32, np.dot with Ti, clip, *255 in
+// float32, truncation toward zero.
+TMF_HD void ycc_to_rgb8_exact(float y, float cb, float cr, uint32_t& R, uint32_t& G, uint32_t& B) {
+  float zb = f_add(cb, -0.5f), zr = f_add(cr, -0.5f);
+  float r = dot3_npdot(1.0, 0.0, 1.403, y, zb, zr);
+  float g = dot3_npdot(1.0, -0.344, -0.714, y, zb, zr);
+  float b = dot3_npdot(1.0, 1.773, 0.0, y, zb, zr);
+  r = fminf(fmaxf(r, 0.0f), 1.0f);
+  g = fminf(fmaxf(g, 0.0f), 1.0f);
+  b = fminf(fmaxf(b, 0.0f), 1.0f);
+  R = (uint32_t)f_mul(r, 255.0f);
+  G = (uint32_t)f_mul(g, 255.0f);
+  B = (uint32_t)f_mul(b, 255.0f);
+}
+
+// ---------------------------------------------------------------------------
+// 8-point orthonormal DCT-II / DCT-III on a strided register vector
+// (even/odd split: 8 add + 32 fma per vector).  C[k][n] = s_k cos(pi(2n+1)k/16),
+// s_0 = sqrt(1/8), s_k = 1/2  - scipy.fftpack.dct(norm="ortho").
+// ---------------------------------------------------------------------------
+#define TMF_C1 0.98078528040323044913f
+#define TMF_C2 0.92387953251128675613f
+#define TMF_C3 0.83146961230254523708f
+#define TMF_C4 0.70710678118654752440f
+#define TMF_C5 0.55557023301960222474f
+#define TMF_C6 0.38268343236508977173f
+#define TMF_C7 0.19509032201612826785f
+#define TMF_G0 0.35355339059327376220f   // sqrt(1/8)
+
+template <int STRIDE>
+TMF_HD void dct8(float* x) {
+  const float s0 = x[0 * STRIDE] + x[7 * STRIDE], d0 = x[0 * STRIDE] - x[7 * STRIDE];
+  const float s1 = x[1 * STRIDE] + x[6 * STRIDE], d1 = x[1 * STRIDE] - x[6 * STRIDE];
+  const float s2 = x[2 * STRIDE] + x[5 * STRIDE], d2 = x[2 * STRIDE] - x[5 * STRIDE];
+  const float s3 = x[3 * STRIDE] + x[4 * STRIDE], d3 = x[3 * STRIDE] - x[4 * STRIDE];
+  const float h = 0.5f;
+  x[0 * STRIDE] = TMF_G0 * ((s0 + s3) + (s1 + s2));
+  x[4 * STRIDE] = (h * TMF_C4) * ((s0 + s3) - (s1 + s2));
+  x[2 * STRIDE] = (h * TMF_C2) * (s0 - s3) + (h * TMF_C6) * (s1 - s2);
+  x[6 * STRIDE] = (h * TMF_C6) * (s0 - s3) - (h * TMF_C2) * (s1 - s2);
+  x[1 * STRIDE] = (h * TMF_C1) * d0 + (h * TMF_C3) * d1 + (h * TMF_C5) * d2 + (h * TMF_C7) * d3;
+  x[3 * STRIDE] = (h * TMF_C3) * d0 - (h * TMF_C7) * d1 - (h * TMF_C1) * d2 - (h * TMF_C5) * d3;
+  x[5 * STRIDE] = (h * TMF_C5) * d0 - (h * TMF_C1) * d1 + (h * TMF_C7) * d2 + (h * TMF_C3) * d3;
+  x[7 * STRIDE] = (h * TMF_C7) * d0 - (h * TMF_C5) * d1 + (h * TMF_C3) * d2 - (h * TMF_C1) * d3;
+}
+
+template <int STRIDE>
+TMF_HD void idct8(float* X) {
+  const float h = 0.5f;
+  const float a = TMF_G0 * X[0 * STRIDE], b = (h * TMF_C4) * X[4 * STRIDE];
+  const float p = a + b, q = a - b;
+  const float u = (h * TMF_C2) * X[2 * STRIDE] + (h * TMF_C6) * X[6 * STRIDE];
+  const float v = (h * TMF_C6) * X[2 * STRIDE] - (h * TMF_C2) * X[6 * STRIDE];
+  const float e0 = p + u, e3 = p - u, e1 = q + v, e2 = q - v;
+  const float x1 = X[1 * STRIDE], x3 = X[3 * STRIDE], x5 = X[5 * STRIDE], x7 = X[7 * STRIDE];
+  const float o0 = (h * TMF_C1) * x1 + (h * TMF_C3) * x3 + (h * TMF_C5) * x5 + (h * TMF_C7) * x7;
+  const float o1 = (h * TMF_C3) * x1 - (h * TMF_C7) * x3 - (h * TMF_C1) * x5 - (h * TMF_C5) * x7;
+  const float o2 = (h * TMF_C5) * x1 - (h * TMF_C1) * x3 + (h * TMF_C7) * x5 + (h * TMF_C3) * x7;
+  const float o3 = (h * TMF_C7) * x1 - (h * TMF_C5) * x3 + (h * TMF_C3) * x5 - (h * TMF_C1) * x7;
+  X[0 * STRIDE] = e0 + o0; X[7 * STRIDE] = e0 - o0;
+  X[1 * STRIDE] = e1 + o1; X[6 * STRIDE] = e1 - o1;
+  X[2 * STRIDE] = e2 + o2; X[5 * STRIDE] = e2 - o2;
+  X[3 * STRIDE] = e3 + o3; X[4 * STRIDE] = e3 - o3;
+}
+
+// 2-D transforms of a row-major 8x8 register block: column pass, then row pass
+// (watermarking.py:78 transforms block.T first, i.e. along the columns).
+TMF_HD void dct8x8(float* a) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dct8<8>(a + j);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dct8<1>(a + 8 * i);
+}
+TMF_HD void idct8x8(float* a) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) idct8<8>(a + j);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) idct8<1>(a + 8 * i);
+}
+
+// ---------------------------------------------------------------------------
+// one-sided (Hestenes) Jacobi SVD of an 8x8 block held in registers.
+//
+// A (row-major, a[8*i+j]) is overwritten by A*V = U*diag(sigma): column k ends
+// as sigma_k * u_k.  V (v[8*i+j]) accumulates the right rotations when WITH_V.
+// Cyclic-by-rows pair order, rotation skipped when the two columns are
+// orthogonal to TOL or when one of them is at the rounding-noise floor of the
+// block.  The block is pre-scaled by an exact power of two so that ||A||_F is
+// in [1, 2) - no underflow in alpha*beta, no overflow for huge inputs; the
+// caller multiplies the column norms by `unscale`.
+//
+// Returns the number of sweeps that performed at least one rotation.
+// ---------------------------------------------------------------------------
+#define TMF_JACOBI_TOL 1.0e-6f
+#define TMF_JACOBI_FLOOR 1.0e-14f      // (eps * ||A||_F)^2 with ||A||_F ~ 1
+#define TMF_JACOBI_MAX_SWEEPS 12
+
+TMF_HD float pow2_scale_for(float frob2, float& unscale) {
+  // frob2 = ||A||_F^2 > 0.  Pick s = 2^-e with e = floor(log2(frob2)/2) so
+  // that frob2*s^2 in [1, 4).  Exponent arithmetic only (exact).
+  int ebits;
+#if defined(__CUDA_ARCH__)
+  ebits = (__float_as_int(frob2) >> 23) & 0xff;
+#else
+  union { float f; int32_t i; } cv; cv.f = frob2; ebits = (cv.i >> 23) & 0xff;
+#endif
+  if (ebits == 0) ebits = 1;                     // denormal / flushed: treat as 2^-126
+  int e2 = ebits - 127;                          // floor(log2(frob2))
+  int e = (e2 >= 0) ? (e2 >> 1) : -((-e2 + 1) >> 1);   // floor(e2 / 2)
+  int se = 127 - e, ue = 127 + e;                // biased exponents of 2^-e and 2^e
+  se = se < 1 ? 1 : (se > 254 ? 254 : se);
+  ue = ue < 1 ? 1 : (ue > 254 ? 254 : ue);
+#if defined(__CUDA_ARCH__)
+  unscale = __int_as_float(ue << 23);
+  return __int_as_float(se << 23);
+#else
+  union { float f; int32_t i; } a, b; a.i = ue << 23; b.i = se << 23; unscale = a.f; return b.f;
+#endif
+}
+
+template <bool WITH_V, int P, int Q>
+TMF_HD bool jacobi_pair(float* a, float* v) {
+  float al = 0.f, be = 0.f, ga = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    al = fmaf(a[8 * i + P], a[8 * i + P], al);
+    be = fmaf(a[8 * i + Q], a[8 * i + Q], be);
+    ga = fmaf(a[8 * i + P], a[8 * i + Q], ga);
+  }
+  const float lim = TMF_JACOBI_TOL * f_sqrt_fast(al * be);
+  const bool rot = (fabsf(ga) > lim) && (fminf(al, be) > TMF_JACOBI_FLOOR);
+  if (rot) {
+    // tan of the rotation angle, smaller root: t = 2g / (d + sign(d) sqrt(d^2 + 4g^2))
+    const float d = be - al, g2 = ga + ga;
+    const float r = f_sqrt_fast(fmaf(g2, g2, d * d));
+    const float t = g2 * f_rcp_fast(d + copysignf(r, d));
+    const float tt = fmaf(t, t, 1.0f);
+    float c = f_rsqrt(tt);
+    c = fmaf(0.5f * c, fmaf(-tt * c, c, 1.0f), c);   // one Newton step: c^2 + s^2 = 1 to ~1 ulp
+    const float s = c * t;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float x = a[8 * i + P], y = a[8 * i + Q];
+      a[8 * i + P] = fmaf(c, x, -s * y);
+      a[8 * i + Q] = fmaf(s, x, c * y);
+    }
+    if (WITH_V) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x = v[8 * i + P], y = v[8 * i + Q];
+        v[8 * i + P] = fmaf(c, x, -s * y);
+        v[8 * i + Q] = fmaf(s, x, c * y);
+      }
+    }
+  }
+  return rot;
+}
+
+template <bool WITH_V, int P, int Q>
+struct JacobiSweep {
+  static TMF_HD bool run(float* a, float* v) {
+    bool r = jacobi_pair<WITH_V, P, Q>(a, v);
+    bool rest = JacobiSweep<WITH_V, (Q == 7 ? P + 1 : P), (Q == 7 ? P + 2 : Q + 1)>::run(a, v);
+    return r || rest;
+  }
+};
+template <bool WITH_V>
+struct JacobiSweep<WITH_V, 7, 8> {
+  static TMF_HD bool run(float*, float*) { return false; }
+};
+
+template <bool WITH_V>
+TMF_HD int jacobi_svd8(float* a, float* v, float& unscale) {
+  float frob2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 64; ++k) frob2 = fmaf(a[k], a[k], frob2);
+  unscale = 1.0f;
+  if (WITH_V) {
+#pragma unroll
+    for (int k = 0; k < 64; ++k) v[k] = ((k >> 3) == (k & 7)) ? 1.0f : 0.0f;
+  }
+  // Inf/NaN input: frob2 is not finite; rotations would only spread NaNs - skip.
+  const bool live = (frob2 > 0.0f) && (frob2 < INFINITY);
+  if (live) {
+    const float s = pow2_scale_for(frob2, unscale);
+#pragma unroll
+    for (int k = 0; k < 64; ++k) a[k] *= s;
+  }
+  int sweeps = 0;
+  bool more = live;
+  for (int it = 0; it < TMF_JACOBI_MAX_SWEEPS && more; ++it) {
+    more = JacobiSweep<WITH_V, 0, 1>::run(a, v);
+    sweeps += more ? 1 : 0;
+  }
+  return sweeps;
+}
+
+// squared column norms of A*V (sigma_k^2 in the scaled domain)
+TMF_HD void column_norms2(const float* a, float* n2) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(a[8 * i + j], a[8 * i + j], s);
+    n2[j] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// whole-block stages shared by the fused kernels and the host test harness
+// ---------------------------------------------------------------------------
+
+// watermarking.py:198 - S[0] += alpha * (wm / 255.0): float32 + float64 product,
+// float64 sum stored back to float32.
+TMF_HD float modulate_sigma0(float s0, double alpha, uint32_t wm_u8) {
+  const double w = d_div((double)wm_u8, 255.0);
+  return (float)((double)s0 + d_mul(alpha, w));
+}
+
+// watermarking.py:285-289 - (S_w[0] - S_o[0]) / alpha in float32 (NumPy >= 2
+// scalar rules), widened to float64, clip [0, 1], * 255 (float64), truncate.
+TMF_HD uint32_t extract_level(float sw, float so, double alpha) {
+  const float e32 = f_div(f_add(sw, -so), (float)alpha);
+  double e = (double)e32;
+  e = e < 0.0 ? 0.0 : (e > 1.0 ? 1.0 : e);
+  return (uint32_t)d_mul(e, 255.0);
+}
+
+// Faithful embed of one luma block held in a[64] (row-major, values in [0,1]):
+// DCT -> Jacobi SVD -> sigma_top += alpha*w -> U diag(S') V^T -> IDCT, in place.
+// v[64] is scratch.  Returns sigma_top (before modulation); *sweeps optional.
+TMF_HD float embed_block_faithful(float* a, float* v, double alpha, uint32_t wm_u8, int* sweeps) {
+  dct8x8(a);
+  float unscale;
+  const int sw = jacobi_svd8<true>(a, v, unscale);
+  if (sweeps) *sweeps = sw;
+#pragma unroll
+  for (int k = 0; k < 64; ++k) a[k] *= unscale;
+  float n2[8];
+  column_norms2(a, n2);
+  float best = n2[0];
+  int top = 0;
+#pragma unroll
+  for (int j = 1; j < 8; ++j) {
+    if (n2[j] > best) { best = n2[j]; top = j; }
+  }
+  const float sig = f_sqrt(best);
+  const float sig_new = modulate_sigma0(sig, alpha, wm_u8);
+  if (sig > 0.0f) {
+    const float f = f_div(sig_new, sig);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sc = (j == top) ? f : 1.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[8 * i + j] *= sc;
+    }
+  } else {
+    a[0] = sig_new;   // all-zero block: LAPACK returns U = V = I, so the mark lands on DC
+  }
+  // M = (A V diag(scale)) V^T, one row at a time, in place
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = a[8 * i + k];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float m = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m = fmaf(t[k], v[8 * j + k], m);
+      a[8 * i + j] = m;
+    }
+  }
+  idct8x8(a);
+  return sig;
+}
+
+// Largest singular value of the DCT of one luma block (extract side).
+TMF_HD float sigma0_block_faithful(float* a, int* sweeps) {
+  dct8x8(a);
+  float unscale;
+  const int sw = jacobi_svd8<false>(a, nullptr, unscale);
+  if (sweeps) *sweeps = sw;
+  float n2[8];
+  column_norms2(a, n2);
+  float best = n2[0];
+#pragma unroll
+  for (int j = 1; j < 8; ++j) best = fmaxf(best, n2[j]);
+  return f_sqrt(best) * unscale;
+}
+
+}  // namespace tmf

@@ -1,0 +1,656 @@
+// libtmfwm: sm_100a kernels + C ABI for the DCT+SVD watermark path.
+// See include/tmf_wm.h for the contract and DESIGN.md for the layout/rooflines.
+//
+// Mapping (faithful mode): ONE THREAD OWNS ONE 8x8 BLOCK.  The block, its DCT,
+// the Jacobi-rotated A*V and V all live in that thread's registers with
+// compile-time indices; there are no shuffles, no shared-memory round trips and
+// no redundant (c, s) computation, so every issue slot does useful fp32 work.
+// Adjacent threads own adjacent blocks of one block-row, so a warp's loads of
+// image row r cover 32*24 = 768 contiguous bytes.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/tmf_wm.h"
+#include "tmf_math.cuh"
+#include "tmf_fast.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TMF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return TMF_OK;
+}
+
+constexpr int kThreads = 128;
+
+// ---------------------------------------------------------------------------
+// 24-byte block-row load/store with the widest access the alignment allows
+// ---------------------------------------------------------------------------
+template <int VEC>
+__device__ __forceinline__ void load_row24(const uint8_t* __restrict__ p, uint32_t (&w)[6]) {
+  if (VEC == 8) {
+    const uint2* q = reinterpret_cast<const uint2*>(p);
+    uint2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y; w[4] = c.x; w[5] = c.y;
+  } else if (VEC == 4) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) w[k] = __ldg(q + k);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      w[k] = (uint32_t)__ldg(p + 4 * k) | ((uint32_t)__ldg(p + 4 * k + 1) << 8) |
+             ((uint32_t)__ldg(p + 4 * k + 2) << 16) | ((uint32_t)__ldg(p + 4 * k + 3) << 24);
+    }
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_row24(uint8_t* __restrict__ p, const uint32_t (&w)[6]) {
+  if (VEC == 8) {
+    uint2* q = reinterpret_cast<uint2*>(p);
+    q[0] = make_uint2(w[0], w[1]); q[1] = make_uint2(w[2], w[3]); q[2] = make_uint2(w[4], w[5]);
+  } else if (VEC == 4) {
+    uint32_t* q = reinterpret_cast<uint32_t*>(p);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) q[k] = w[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 24; ++k) p[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+  }
+}
+
+// byte B (0..23) of a 24-byte row held in six words
+#define TMF_BYTE(w, B) (((w)[(B) >> 2] >> (8 * ((B)&3))) & 0xffu)
+
+struct BlockGeom {
+  int h, w, nbh, nbw;
+  long long blocks_per_img;   // nbh * nbw
+  long long total_blocks;     // n * blocks_per_img
+  size_t img_stride;          // bytes between images
+  size_t row_pitch;           // 3 * w
+};
+
+__device__ __forceinline__ size_t block_origin(const BlockGeom& g, long long gb, long long& img, int& by, int& bx) {
+  img = gb / g.blocks_per_img;
+  const int r = (int)(gb - img * g.blocks_per_img);
+  by = r / g.nbw;
+  bx = r - by * g.nbw;
+  return (size_t)img * g.img_stride + (size_t)by * 8 * g.row_pitch + (size_t)bx * 24;
+}
+
+template <int VEC>
+__device__ __forceinline__ void load_luma_block(const uint8_t* __restrict__ base, size_t pitch, float* a) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint32_t w[6];
+    load_row24<VEC>(base + (size_t)i * pitch, w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float r = tmf::unit_from_u8(TMF_BYTE(w, 3 * j));
+      const float g = tmf::unit_from_u8(TMF_BYTE(w, 3 * j + 1));
+      const float b = tmf::unit_from_u8(TMF_BYTE(w, 3 * j + 2));
+      a[8 * i + j] = tmf::luma_exact(r, g, b);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// fused embed, faithful mode (watermarking.py:163-219 in one launch)
+// ---------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_embed_faithful(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGeom g,
+                 const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
+  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (gb >= g.total_blocks) return;
+  long long img; int by, bx;
+  const size_t org = block_origin(g, gb, img, by, bx);
+  const uint8_t* src = rgb + org;
+
+  float a[64], v[64];
+  load_luma_block<VEC>(src, g.row_pitch, a);
+  const long long wi = (wm_shared ? 0 : img * g.blocks_per_img) + (long long)by * g.nbw + bx;
+  tmf::embed_block_faithful(a, v, alpha, (uint32_t)__ldg(wm + wi), nullptr);
+
+  // colour out: chroma is recomputed from the (L1/L2-resident) input bytes
+  uint8_t* dst = out + org;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint32_t w[6], o[6] = {0, 0, 0, 0, 0, 0};
+    load_row24<VEC>(src + (size_t)i * g.row_pitch, w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float r = tmf::unit_from_u8(TMF_BYTE(w, 3 * j));
+      const float gg = tmf::unit_from_u8(TMF_BYTE(w, 3 * j + 1));
+      const float b = tmf::unit_from_u8(TMF_BYTE(w, 3 * j + 2));
+      float cb, cr;
+      tmf::chroma_exact(r, gg, b, cb, cr);
+      uint32_t R, G, B;
+      tmf::ycc_to_rgb8_exact(a[8 * i + j], cb, cr, R, G, B);
+      o[(3 * j) >> 2] |= R << (8 * ((3 * j) & 3));
+      o[(3 * j + 1) >> 2] |= G << (8 * ((3 * j + 1) & 3));
+      o[(3 * j + 2) >> 2] |= B << (8 * ((3 * j + 2) & 3));
+    }
+    store_row24<VEC>(dst + (size_t)i * g.row_pitch, o);
+  }
+}
+
+// pixels outside whole blocks: colour round trip only (watermarking.py:173-174, :216)
+__global__ void __launch_bounds__(256)
+k_strip_roundtrip(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGeom g, int n,
+                  long long strip_px_per_img) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= strip_px_per_img * n) return;
+  const long long img = t / strip_px_per_img;
+  long long idx = t - img * strip_px_per_img;
+  const int bw = g.nbw * 8, bh = g.nbh * 8, rw = g.w - bw;
+  int y, x;
+  if (idx < (long long)g.h * rw) {
+    y = (int)(idx / rw);
+    x = bw + (int)(idx - (long long)y * rw);
+  } else {
+    idx -= (long long)g.h * rw;
+    y = bh + (int)(idx / bw);
+    x = (int)(idx - (long long)(y - bh) * bw);
+  }
+  const size_t off = (size_t)img * g.img_stride + (size_t)y * g.row_pitch + (size_t)x * 3;
+  const float r = tmf::unit_from_u8(__ldg(rgb + off));
+  const float gg = tmf::unit_from_u8(__ldg(rgb + off + 1));
+  const float b = tmf::unit_from_u8(__ldg(rgb + off + 2));
+  float cb, cr;
+  tmf::chroma_exact(r, gg, b, cb, cr);
+  uint32_t R, G, B;
+  tmf::ycc_to_rgb8_exact(tmf::luma_exact(r, gg, b), cb, cr, R, G, B);
+  out[off] = (uint8_t)R; out[off + 1] = (uint8_t)G; out[off + 2] = (uint8_t)B;
+}
+
+// ---------------------------------------------------------------------------
+// fused extract, faithful mode (watermarking.py:246-289 in one launch)
+// ---------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_extract_faithful(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ orig, uint8_t* __restrict__ out_wm,
+                   BlockGeom g, double alpha) {
+  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (gb >= g.total_blocks) return;
+  long long img; int by, bx;
+  const size_t org = block_origin(g, gb, img, by, bx);
+  float a[64];
+  load_luma_block<VEC>(wmk + org, g.row_pitch, a);
+  const float sw = tmf::sigma0_block_faithful(a, nullptr);
+  load_luma_block<VEC>(orig + org, g.row_pitch, a);
+  const float so = tmf::sigma0_block_faithful(a, nullptr);
+  out_wm[gb] = (uint8_t)tmf::extract_level(sw, so, alpha);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_sigma0_faithful(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, BlockGeom g) {
+  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (gb >= g.total_blocks) return;
+  long long img; int by, bx;
+  const size_t org = block_origin(g, gb, img, by, bx);
+  float a[64];
+  load_luma_block<VEC>(rgb + org, g.row_pitch, a);
+  sigma0[gb] = tmf::sigma0_block_faithful(a, nullptr);
+}
+
+// ---------------------------------------------------------------------------
+// FAST mode kernels (tmf_fast.cuh): same one-thread-per-block mapping, spatial
+// top-triplet instead of DCT + full SVD, fp32 colour in 0..255 units
+// ---------------------------------------------------------------------------
+// byte B of the 24-byte row as a float, via the 2^23 magic number (PRMT + FADD,
+// both full-rate pipes; the I2F.U8 conversion pipe is much narrower)
+__device__ __forceinline__ float byte_to_float(const uint32_t (&w)[6], int B) {
+  const uint32_t m = __byte_perm(w[B >> 2], 0x4B000000u, 0x7650u | (uint32_t)(B & 3));
+  return __uint_as_float(m) - 8388608.0f;
+}
+
+template <int VEC>
+__device__ __forceinline__ void load_luma255_block(const uint8_t* __restrict__ base, size_t pitch, float* a) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint32_t w[6];
+    load_row24<VEC>(base + (size_t)i * pitch, w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      a[8 * i + j] = tmf::luma255_fast(byte_to_float(w, 3 * j), byte_to_float(w, 3 * j + 1), byte_to_float(w, 3 * j + 2));
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGeom g,
+             const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
+  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (gb >= g.total_blocks) return;
+  long long img; int by, bx;
+  const size_t org = block_origin(g, gb, img, by, bx);
+  const uint8_t* src = rgb + org;
+  float a[64];
+  load_luma255_block<VEC>(src, g.row_pitch, a);
+  const long long wi = (wm_shared ? 0 : img * g.blocks_per_img) + (long long)by * g.nbw + bx;
+  tmf::embed_block_fast(a, alpha, (uint32_t)__ldg(wm + wi), nullptr);
+  uint8_t* dst = out + org;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint32_t w[6], o[6] = {0, 0, 0, 0, 0, 0};
+    load_row24<VEC>(src + (size_t)i * g.row_pitch, w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float R, G, B;
+      tmf::rgb255_out_fast(byte_to_float(w, 3 * j), byte_to_float(w, 3 * j + 1), byte_to_float(w, 3 * j + 2),
+                           a[8 * i + j], R, G, B);
+      o[(3 * j) >> 2] |= tmf::quant255(R) << (8 * ((3 * j) & 3));
+      o[(3 * j + 1) >> 2] |= tmf::quant255(G) << (8 * ((3 * j + 1) & 3));
+      o[(3 * j + 2) >> 2] |= tmf::quant255(B) << (8 * ((3 * j + 2) & 3));
+    }
+    store_row24<VEC>(dst + (size_t)i * g.row_pitch, o);
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_extract_fast(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ orig, uint8_t* __restrict__ out_wm,
+               BlockGeom g, double alpha) {
+  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (gb >= g.total_blocks) return;
+  long long img; int by, bx;
+  const size_t org = block_origin(g, gb, img, by, bx);
+  float a[64];
+  load_luma255_block<VEC>(wmk + org, g.row_pitch, a);
+  const float sw = tmf::sigma0_block_fast(a, nullptr);
+  load_luma255_block<VEC>(orig + org, g.row_pitch, a);
+  const float so = tmf::sigma0_block_fast(a, nullptr);
+  out_wm[gb] = (uint8_t)tmf::extract_level(sw, so, alpha);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_sigma0_fast(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, BlockGeom g) {
+  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (gb >= g.total_blocks) return;
+  long long img; int by, bx;
+  const size_t org = block_origin(g, gb, img, by, bx);
+  float a[64];
+  load_luma255_block<VEC>(rgb + org, g.row_pitch, a);
+  sigma0[gb] = tmf::sigma0_block_fast(a, nullptr);
+}
+
+// ---------------------------------------------------------------------------
+// standalone batched SVD / DCT / colour taps
+// ---------------------------------------------------------------------------
+constexpr int kPad = 65;   // smem row stride (floats) for a 64-float block: conflict-free both ways
+
+__device__ __forceinline__ void cswap_cols(float* s, float* a, float* v, bool with_v, int i, int j) {
+  // order so that s[i] >= s[j]
+  const bool sw = s[i] < s[j];
+  const float si = s[i], sj = s[j];
+  s[i] = sw ? sj : si; s[j] = sw ? si : sj;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const float x = a[8 * r + i], y = a[8 * r + j];
+    a[8 * r + i] = sw ? y : x; a[8 * r + j] = sw ? x : y;
+  }
+  if (with_v) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float x = v[8 * r + i], y = v[8 * r + j];
+      v[8 * r + i] = sw ? y : x; v[8 * r + j] = sw ? x : y;
+    }
+  }
+}
+
+// Complete the columns of U (row-major u[8*r+c] in LOCAL memory) flagged in
+// `null_mask` to an orthonormal basis: twice-iterated Gram-Schmidt of the unit
+// vectors e_0..e_7 against the columns already fixed.  Rare path (rank-deficient
+// blocks only), so dynamic indexing / local memory is acceptable here.
+__device__ __noinline__ void complete_u_columns(float* u, unsigned null_mask) {
+  unsigned fixed = (~null_mask) & 0xffu;
+  int cand = 0;
+  for (int k = 0; k < 8; ++k) {
+    if (!((null_mask >> k) & 1u)) continue;
+    for (; cand < 8; ++cand) {
+      float wv[8];
+      for (int r = 0; r < 8; ++r) wv[r] = (r == cand) ? 1.0f : 0.0f;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int c = 0; c < 8; ++c) {
+          if (!((fixed >> c) & 1u)) continue;
+          float d = 0.f;
+          for (int r = 0; r < 8; ++r) d = fmaf(u[8 * r + c], wv[r], d);
+          for (int r = 0; r < 8; ++r) wv[r] = fmaf(-d, u[8 * r + c], wv[r]);
+        }
+      }
+      float n2 = 0.f;
+      for (int r = 0; r < 8; ++r) n2 = fmaf(wv[r], wv[r], n2);
+      if (n2 > 0.25f) {
+        const float inv = rsqrtf(n2);
+        for (int r = 0; r < 8; ++r) u[8 * r + k] = wv[r] * inv;
+        fixed |= 1u << k;
+        ++cand;
+        break;
+      }
+    }
+  }
+}
+
+template <bool WITH_UV>
+__global__ void __launch_bounds__(kThreads)
+k_svd8x8(const float* __restrict__ blocks, long long nblocks, float* __restrict__ S, float* __restrict__ U,
+         float* __restrict__ Vt, int* __restrict__ sweeps_out, int complete_u) {
+  __shared__ float sm[kThreads * kPad];
+  const long long b0 = (long long)blockIdx.x * kThreads;
+  const int nb = (int)min((long long)kThreads, nblocks - b0);
+  const int t = threadIdx.x;
+
+  // coalesced stage-in
+  const float* src = blocks + b0 * 64;
+  for (int idx = t; idx < nb * 64; idx += kThreads) sm[(idx >> 6) * kPad + (idx & 63)] = __ldg(src + idx);
+  __syncthreads();
+
+  float a[64], v[WITH_UV ? 64 : 1], s[8];
+  int sweeps = 0;
+  float unscale = 1.0f;
+  unsigned null_mask = 0;
+  if (t < nb) {
+#pragma unroll
+    for (int k = 0; k < 64; ++k) a[k] = sm[t * kPad + k];
+    sweeps = tmf::jacobi_svd8<WITH_UV>(a, v, unscale);
+    float n2[8];
+    tmf::column_norms2(a, n2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = tmf::f_sqrt(n2[j]);   // scaled domain
+    // 19-comparator sorting network, descending
+#define CS(i, j) cswap_cols(s, a, v, WITH_UV, i, j)
+    CS(0, 1); CS(2, 3); CS(4, 5); CS(6, 7);
+    CS(0, 2); CS(1, 3); CS(4, 6); CS(5, 7);
+    CS(1, 2); CS(5, 6); CS(0, 4); CS(3, 7);
+    CS(1, 5); CS(2, 6);
+    CS(1, 4); CS(3, 6);
+    CS(2, 4); CS(3, 5);
+    CS(3, 4);
+#undef CS
+    if (WITH_UV) {
+      // U = (A V) diag(1/sigma); columns at the noise floor are zeroed (or completed below)
+      const float thr = 1.0e-6f * s[0];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = s[j] > thr;
+        null_mask |= ok ? 0u : (1u << j);
+        const float inv = ok ? tmf::f_div(1.0f, s[j]) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[8 * i + j] *= inv;
+      }
+      if (s[0] == 0.0f) null_mask = 0xffu;
+    }
+  }
+  __syncthreads();
+
+  // S out
+  if (t < nb) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[t * 9 + j] = s[j] * unscale;
+  }
+  __syncthreads();
+  for (int idx = t; idx < nb * 8; idx += kThreads) S[b0 * 8 + idx] = sm[(idx >> 3) * 9 + (idx & 7)];
+  if (sweeps_out && t < nb) sweeps_out[b0 + t] = sweeps;
+  if (!WITH_UV) return;
+  __syncthreads();
+
+  // U out
+  if (t < nb) {
+    if (complete_u && null_mask) {
+      float u[64];
+#pragma unroll
+      for (int k = 0; k < 64; ++k) u[k] = a[k];
+      complete_u_columns(u, null_mask);
+#pragma unroll
+      for (int k = 0; k < 64; ++k) a[k] = u[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 64; ++k) sm[t * kPad + k] = a[k];
+  }
+  __syncthreads();
+  for (int idx = t; idx < nb * 64; idx += kThreads) U[b0 * 64 + idx] = sm[(idx >> 6) * kPad + (idx & 63)];
+  __syncthreads();
+  // Vt out: Vt[k][j] = V[j][k]
+  if (t < nb) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sm[t * kPad + 8 * k + j] = v[WITH_UV ? 8 * j + k : 0];
+  }
+  __syncthreads();
+  for (int idx = t; idx < nb * 64; idx += kThreads) Vt[b0 * 64 + idx] = sm[(idx >> 6) * kPad + (idx & 63)];
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_dct8x8(const float* __restrict__ in, float* __restrict__ out, long long nblocks, int inverse) {
+  __shared__ float sm[kThreads * kPad];
+  const long long b0 = (long long)blockIdx.x * kThreads;
+  const int nb = (int)min((long long)kThreads, nblocks - b0);
+  const int t = threadIdx.x;
+  for (int idx = t; idx < nb * 64; idx += kThreads) sm[(idx >> 6) * kPad + (idx & 63)] = __ldg(in + b0 * 64 + idx);
+  __syncthreads();
+  if (t < nb) {
+    float a[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) a[k] = sm[t * kPad + k];
+    if (inverse) tmf::idct8x8(a); else tmf::dct8x8(a);
+#pragma unroll
+    for (int k = 0; k < 64; ++k) sm[t * kPad + k] = a[k];
+  }
+  __syncthreads();
+  for (int idx = t; idx < nb * 64; idx += kThreads) out[b0 * 64 + idx] = sm[(idx >> 6) * kPad + (idx & 63)];
+}
+
+__global__ void __launch_bounds__(256)
+k_rgb2ycc(const uint8_t* __restrict__ rgb, float* __restrict__ ycc, long long npx) {
+  const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= npx) return;
+  const float r = tmf::unit_from_u8(__ldg(rgb + 3 * p));
+  const float g = tmf::unit_from_u8(__ldg(rgb + 3 * p + 1));
+  const float b = tmf::unit_from_u8(__ldg(rgb + 3 * p + 2));
+  float cb, cr;
+  tmf::chroma_exact(r, g, b, cb, cr);
+  ycc[3 * p] = tmf::luma_exact(r, g, b);
+  ycc[3 * p + 1] = cb;
+  ycc[3 * p + 2] = cr;
+}
+
+__global__ void __launch_bounds__(256)
+k_ycc2rgb(const float* __restrict__ ycc, uint8_t* __restrict__ rgb, long long npx) {
+  const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= npx) return;
+  uint32_t R, G, B;
+  tmf::ycc_to_rgb8_exact(__ldg(ycc + 3 * p), __ldg(ycc + 3 * p + 1), __ldg(ycc + 3 * p + 2), R, G, B);
+  rgb[3 * p] = (uint8_t)R; rgb[3 * p + 1] = (uint8_t)G; rgb[3 * p + 2] = (uint8_t)B;
+}
+
+// ---------------------------------------------------------------------------
+// host-side helpers
+// ---------------------------------------------------------------------------
+int make_geom(int n, int h, int w, size_t img_stride, int block, BlockGeom& g) {
+  if (block != 8)
+    return fail(TMF_ERR_UNSUPPORTED_BLOCK,
+                "block_size %d is not supported: this build implements the reference's BLOCK_SIZE = 8 only "
+                "(there is no CPU fallback)", block);
+  if (n < 0 || h < 0 || w < 0) return fail(TMF_ERR_BAD_ARG, "negative dimension (n=%d h=%d w=%d)", n, h, w);
+  if (n > 0 && img_stride < (size_t)h * w * 3)
+    return fail(TMF_ERR_BAD_ARG, "img_stride %zu is smaller than one image (%zu bytes)", img_stride, (size_t)h * w * 3);
+  g.h = h; g.w = w; g.nbh = h / 8; g.nbw = w / 8;
+  g.blocks_per_img = (long long)g.nbh * g.nbw;
+  g.total_blocks = g.blocks_per_img * n;
+  g.img_stride = img_stride;
+  g.row_pitch = (size_t)w * 3;
+  return TMF_OK;
+}
+
+int pick_vec(const BlockGeom& g, const void* p0, const void* p1, const void* p2 = nullptr) {
+  uintptr_t bits = (uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2 | (uintptr_t)g.img_stride | (uintptr_t)g.row_pitch;
+  if ((bits & 7) == 0) return 8;
+  if ((bits & 3) == 0) return 4;
+  return 1;
+}
+
+unsigned grid_for(long long items, int per_cta) { return (unsigned)((items + per_cta - 1) / per_cta); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int tmf_version(void) { return TMF_VERSION; }
+const char* tmf_last_error(void) { return g_err; }
+
+int tmf_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(TMF_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+  return n;
+}
+
+int tmf_embed_rgb8(const uint8_t* rgb, uint8_t* out, int n, int h, int w, size_t img_stride, const uint8_t* wm,
+                   int wm_shared, double alpha, int block, int mode, void* stream) {
+  BlockGeom g;
+  if (int rc = make_geom(n, h, w, img_stride, block, g)) return rc;
+  if (mode != TMF_MODE_FAITHFUL && mode != TMF_MODE_FAST) return fail(TMF_ERR_BAD_ARG, "unknown mode %d", mode);
+  if (n == 0 || h == 0 || w == 0) return TMF_OK;
+  if (!rgb || !out) return fail(TMF_ERR_BAD_ARG, "null image pointer");
+  if (rgb == out) return fail(TMF_ERR_BAD_ARG, "out must not alias rgb");
+  if (g.total_blocks > 0 && !wm) return fail(TMF_ERR_BAD_ARG, "null watermark map");
+  if (!(alpha == alpha)) return fail(TMF_ERR_BAD_ARG, "alpha is NaN");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g.total_blocks > 0) {
+    const unsigned grid = grid_for(g.total_blocks, kThreads);
+    const int vec = pick_vec(g, rgb, out);
+    if (mode == TMF_MODE_FAST) {
+      switch (vec) {
+        case 8: k_embed_fast<8><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
+        case 4: k_embed_fast<4><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
+        default: k_embed_fast<1><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
+      }
+    } else {
+      switch (vec) {
+        case 8: k_embed_faithful<8><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
+        case 4: k_embed_faithful<4><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
+        default: k_embed_faithful<1><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
+      }
+    }
+    if (int rc = check_launch("embed kernel launch")) return rc;
+  }
+  const long long strip = (long long)h * w - g.blocks_per_img * 64;
+  if (strip > 0) {
+    k_strip_roundtrip<<<grid_for(strip * n, 256), 256, 0, st>>>(rgb, out, g, n, strip);
+    if (int rc = check_launch("strip kernel launch")) return rc;
+  }
+  return TMF_OK;
+}
+
+int tmf_extract_rgb8(const uint8_t* wmk_rgb, const uint8_t* orig_rgb, uint8_t* out_wm, int n, int h, int w,
+                     size_t img_stride, double alpha, int block, int mode, void* stream) {
+  BlockGeom g;
+  if (int rc = make_geom(n, h, w, img_stride, block, g)) return rc;
+  if (mode != TMF_MODE_FAITHFUL && mode != TMF_MODE_FAST) return fail(TMF_ERR_BAD_ARG, "unknown mode %d", mode);
+  if (g.total_blocks == 0) return TMF_OK;
+  if (!wmk_rgb || !orig_rgb || !out_wm) return fail(TMF_ERR_BAD_ARG, "null pointer");
+  if (!(alpha == alpha) || alpha == 0.0) return fail(TMF_ERR_BAD_ARG, "alpha must be a non-zero number");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = grid_for(g.total_blocks, kThreads);
+  const int vec = pick_vec(g, wmk_rgb, orig_rgb);
+  if (mode == TMF_MODE_FAST) {
+    switch (vec) {
+      case 8: k_extract_fast<8><<<grid, kThreads, 0, st>>>(wmk_rgb, orig_rgb, out_wm, g, alpha); break;
+      case 4: k_extract_fast<4><<<grid, kThreads, 0, st>>>(wmk_rgb, orig_rgb, out_wm, g, alpha); break;
+      default: k_extract_fast<1><<<grid, kThreads, 0, st>>>(wmk_rgb, orig_rgb, out_wm, g, alpha); break;
+    }
+  } else {
+    switch (vec) {
+      case 8: k_extract_faithful<8><<<grid, kThreads, 0, st>>>(wmk_rgb, orig_rgb, out_wm, g, alpha); break;
+      case 4: k_extract_faithful<4><<<grid, kThreads, 0, st>>>(wmk_rgb, orig_rgb, out_wm, g, alpha); break;
+      default: k_extract_faithful<1><<<grid, kThreads, 0, st>>>(wmk_rgb, orig_rgb, out_wm, g, alpha); break;
+    }
+  }
+  return check_launch("extract kernel launch");
+}
+
+int tmf_sigma0_rgb8(const uint8_t* rgb, float* sigma0, int n, int h, int w, size_t img_stride, int block, int mode,
+                    void* stream) {
+  BlockGeom g;
+  if (int rc = make_geom(n, h, w, img_stride, block, g)) return rc;
+  if (mode != TMF_MODE_FAITHFUL && mode != TMF_MODE_FAST) return fail(TMF_ERR_BAD_ARG, "unknown mode %d", mode);
+  if (g.total_blocks == 0) return TMF_OK;
+  if (!rgb || !sigma0) return fail(TMF_ERR_BAD_ARG, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = grid_for(g.total_blocks, kThreads);
+  const int vec = pick_vec(g, rgb, rgb);
+  if (mode == TMF_MODE_FAST) {
+    switch (vec) {
+      case 8: k_sigma0_fast<8><<<grid, kThreads, 0, st>>>(rgb, sigma0, g); break;
+      case 4: k_sigma0_fast<4><<<grid, kThreads, 0, st>>>(rgb, sigma0, g); break;
+      default: k_sigma0_fast<1><<<grid, kThreads, 0, st>>>(rgb, sigma0, g); break;
+    }
+  } else {
+    switch (vec) {
+      case 8: k_sigma0_faithful<8><<<grid, kThreads, 0, st>>>(rgb, sigma0, g); break;
+      case 4: k_sigma0_faithful<4><<<grid, kThreads, 0, st>>>(rgb, sigma0, g); break;
+      default: k_sigma0_faithful<1><<<grid, kThreads, 0, st>>>(rgb, sigma0, g); break;
+    }
+  }
+  return check_launch("sigma0 kernel launch");
+}
+
+int tmf_svd8x8_f32(const float* blocks, int64_t nblocks, float* S, float* U, float* Vt, int32_t* sweeps,
+                   int complete_u, void* stream) {
+  if (nblocks < 0) return fail(TMF_ERR_BAD_ARG, "negative block count");
+  if (nblocks == 0) return TMF_OK;
+  if (!blocks || !S) return fail(TMF_ERR_BAD_ARG, "null pointer");
+  if ((U == nullptr) != (Vt == nullptr)) return fail(TMF_ERR_BAD_ARG, "U and Vt must both be given or both be NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = grid_for(nblocks, kThreads);
+  if (U) k_svd8x8<true><<<grid, kThreads, 0, st>>>(blocks, nblocks, S, U, Vt, sweeps, complete_u);
+  else k_svd8x8<false><<<grid, kThreads, 0, st>>>(blocks, nblocks, S, nullptr, nullptr, sweeps, 0);
+  return check_launch("svd kernel launch");
+}
+
+int tmf_dct8x8_f32(const float* in, float* out, int64_t nblocks, int inverse, void* stream) {
+  if (nblocks < 0) return fail(TMF_ERR_BAD_ARG, "negative block count");
+  if (nblocks == 0) return TMF_OK;
+  if (!in || !out) return fail(TMF_ERR_BAD_ARG, "null pointer");
+  k_dct8x8<<<grid_for(nblocks, kThreads), kThreads, 0, (cudaStream_t)stream>>>(in, out, nblocks, inverse ? 1 : 0);
+  return check_launch("dct kernel launch");
+}
+
+int tmf_rgb8_to_ycbcr_f32(const uint8_t* rgb, float* ycc, int64_t npixels, void* stream) {
+  if (npixels < 0) return fail(TMF_ERR_BAD_ARG, "negative pixel count");
+  if (npixels == 0) return TMF_OK;
+  if (!rgb || !ycc) return fail(TMF_ERR_BAD_ARG, "null pointer");
+  k_rgb2ycc<<<grid_for(npixels, 256), 256, 0, (cudaStream_t)stream>>>(rgb, ycc, npixels);
+  return check_launch("rgb->ycbcr kernel launch");
+}
+
+int tmf_ycbcr_f32_to_rgb8(const float* ycc, uint8_t* rgb, int64_t npixels, void* stream) {
+  if (npixels < 0) return fail(TMF_ERR_BAD_ARG, "negative pixel count");
+  if (npixels == 0) return TMF_OK;
+  if (!ycc || !rgb) return fail(TMF_ERR_BAD_ARG, "null pointer");
+  k_ycc2rgb<<<grid_for(npixels, 256), 256, 0, (cudaStream_t)stream>>>(ycc, rgb, npixels);
+  return check_launch("ycbcr->rgb kernel launch");
+}
+
+}  // extern "C"

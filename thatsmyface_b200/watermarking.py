@@ -1,0 +1,356 @@
+"""Drop-in replacement for the reference's ``modules/watermarking.py``.
+
+Same public names, signatures, argument meaning and error behaviour as the
+reference (Rigelyon/ThatsMyFace ``modules/watermarking.py``), with the per-pixel
+and per-block NumPy/SciPy loops replaced by one fused sm_100a kernel launch
+through the C ABI in ``include/tmf_wm.h``:
+
+=========================  =====================================  ====================
+reference function         lines                                  here
+=========================  =====================================  ====================
+``get_watermark_settings``  ``modules/watermarking.py:10-20``      same precedence
+``rgb_to_ycbcr``            ``:23-50``                             ``tmf_rgb8_to_ycbcr_f32``
+``ycbcr_to_rgb``            ``:53-73``                             ``tmf_ycbcr_f32_to_rgb8``
+``apply_dct_to_block``      ``:76-78``                             ``tmf_dct8x8_f32``
+``apply_idct_to_block``     ``:81-83``                             ``tmf_dct8x8_f32`` (inverse)
+``resize_watermark``        ``:86-132``                            host (PIL), unchanged semantics
+``embed_watermark``         ``:135-221``                           ``tmf_embed_rgb8``
+``extract_watermark``       ``:224-294``                           ``tmf_extract_rgb8``
+=========================  =====================================  ====================
+
+PyTorch is used only for device memory, streams and pinned staging.  There is
+no CPU fallback: without a CUDA device, or without ``libtmfwm.so``, every
+compute entry point raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import io
+import sys
+from typing import Optional, Sequence
+
+import numpy as np
+from PIL import Image
+
+from . import _lib
+from .constants import ALPHA, BLOCK_SIZE, MODE_FAITHFUL, MODE_FAST
+
+__all__ = [
+    "get_watermark_settings", "rgb_to_ycbcr", "ycbcr_to_rgb", "apply_dct_to_block",
+    "apply_idct_to_block", "resize_watermark", "embed_watermark", "extract_watermark",
+    "embed_tensor", "extract_tensor", "sigma0_tensor", "svd8x8", "dct8x8",
+    "embed_watermark_batch", "extract_watermark_batch",
+]
+
+#: mode used when neither ``custom_settings["mode"]`` nor an explicit argument says otherwise
+DEFAULT_MODE = MODE_FAITHFUL
+
+
+# ---------------------------------------------------------------------------
+# settings (watermarking.py:10-20, :149-151, :237-239)
+# ---------------------------------------------------------------------------
+def _session_settings():
+    """``st.session_state.custom_settings`` if Streamlit is loaded in this
+    process and the key exists, else None.  Streamlit is never imported by us:
+    the reference's pages import it before they call into this module, and
+    outside the app (tests, batch jobs) there is no session to read."""
+    st = sys.modules.get("streamlit")
+    if st is None:
+        return None
+    try:
+        state = st.session_state
+        if "custom_settings" in state:
+            return state["custom_settings"] if isinstance(state, dict) else state.custom_settings
+    except Exception:
+        return None
+    return None
+
+
+def get_watermark_settings():
+    s = _session_settings()
+    if s is not None:
+        return {"block_size": s.get("block_size", BLOCK_SIZE), "alpha": s.get("alpha", ALPHA)}
+    return {"block_size": BLOCK_SIZE, "alpha": ALPHA}
+
+
+def _resolve(custom_settings):
+    settings = custom_settings if custom_settings else get_watermark_settings()
+    return (settings.get("block_size", BLOCK_SIZE), settings.get("alpha", ALPHA),
+            settings.get("mode", DEFAULT_MODE))
+
+
+# ---------------------------------------------------------------------------
+# device plumbing
+# ---------------------------------------------------------------------------
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "thatsmyface_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback "
+            "for the watermark path"
+        )
+    return torch
+
+
+def _stream_ptr(torch):
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_u8_images(t, name):
+    torch = _torch()
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.uint8):
+        raise ValueError(f"{name} must be a CUDA uint8 tensor")
+    if t.dim() == 3:
+        t = t.unsqueeze(0)
+    if t.dim() != 4 or t.shape[-1] != 3:
+        raise ValueError(f"{name} must have shape (N, H, W, 3) or (H, W, 3), got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def embed_tensor(rgb, wm, alpha=ALPHA, block_size=BLOCK_SIZE, mode=None, out=None):
+    """Fused embed on device-resident images.
+
+    ``rgb``: CUDA uint8 ``(N, H, W, 3)`` (or ``(H, W, 3)``).  ``wm``: CUDA uint8
+    watermark map ``(H//8, W//8)`` shared by the batch, or ``(N, H//8, W//8)``.
+    Returns a CUDA uint8 tensor shaped like ``rgb``.  Asynchronous on the current
+    stream."""
+    torch = _torch()
+    squeeze = rgb.dim() == 3
+    x = _check_u8_images(rgb, "rgb")
+    n, h, w, _ = x.shape
+    nbh, nbw = h // 8, w // 8
+    if not (isinstance(wm, torch.Tensor) and wm.is_cuda and wm.dtype == torch.uint8):
+        raise ValueError("wm must be a CUDA uint8 tensor")
+    wm = wm.contiguous()
+    if tuple(wm.shape) == (nbh, nbw):
+        shared = 1
+    elif tuple(wm.shape) == (n, nbh, nbw):
+        shared = 0
+    else:
+        raise ValueError(f"watermark map must be {(nbh, nbw)} or {(n, nbh, nbw)}, got {tuple(wm.shape)}")
+    if out is None:
+        out = torch.empty_like(x)
+    elif out.shape != x.shape or out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous():
+        raise ValueError("out must be a contiguous CUDA uint8 tensor shaped like rgb")
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.tmf_embed_rgb8(x.data_ptr(), out.data_ptr(), n, h, w, h * w * 3, wm.data_ptr(), shared,
+                                      float(alpha), int(block_size), int(DEFAULT_MODE if mode is None else mode),
+                                      _stream_ptr(torch)))
+    return out[0] if squeeze else out
+
+
+def extract_tensor(wmk, orig, alpha=ALPHA, block_size=BLOCK_SIZE, mode=None, out=None):
+    """Fused extract on device-resident images -> CUDA uint8 ``(N, H//8, W//8)``."""
+    torch = _torch()
+    squeeze = wmk.dim() == 3
+    a = _check_u8_images(wmk, "watermarked")
+    b = _check_u8_images(orig, "original")
+    if a.shape != b.shape:
+        raise ValueError(f"watermarked {tuple(a.shape)} and original {tuple(b.shape)} images must have the same shape")
+    if a.device != b.device:
+        raise ValueError("watermarked and original images must be on the same device")
+    n, h, w, _ = a.shape
+    if out is None:
+        out = torch.empty((n, h // 8, w // 8), dtype=torch.uint8, device=a.device)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        _lib.check(lib.tmf_extract_rgb8(a.data_ptr(), b.data_ptr(), out.data_ptr(), n, h, w, h * w * 3,
+                                        float(alpha), int(block_size), int(DEFAULT_MODE if mode is None else mode),
+                                        _stream_ptr(torch)))
+    return out[0] if squeeze else out
+
+
+def sigma0_tensor(rgb, block_size=BLOCK_SIZE, mode=None):
+    """Tap: largest singular value per luma block, CUDA float32 ``(N, H//8, W//8)``."""
+    torch = _torch()
+    squeeze = rgb.dim() == 3
+    x = _check_u8_images(rgb, "rgb")
+    n, h, w, _ = x.shape
+    out = torch.empty((n, h // 8, w // 8), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.tmf_sigma0_rgb8(x.data_ptr(), out.data_ptr(), n, h, w, h * w * 3, int(block_size),
+                                       int(DEFAULT_MODE if mode is None else mode), _stream_ptr(torch)))
+    return out[0] if squeeze else out
+
+
+def svd8x8(blocks, vectors=True, complete_u=False, return_sweeps=False):
+    """Batched one-sided-Jacobi SVD of CUDA float32 ``(..., 8, 8)`` blocks
+    (``np.linalg.svd(block, full_matrices=True)`` of watermarking.py:195).
+    Returns ``(U, S, Vt)`` like NumPy, or ``S`` when ``vectors=False``."""
+    torch = _torch()
+    if not (isinstance(blocks, torch.Tensor) and blocks.is_cuda and blocks.dtype == torch.float32):
+        raise ValueError("blocks must be a CUDA float32 tensor")
+    if blocks.shape[-2:] != (8, 8):
+        raise ValueError("only 8x8 blocks are supported (the reference's BLOCK_SIZE); no CPU fallback")
+    lead = blocks.shape[:-2]
+    x = blocks.reshape(-1, 8, 8).contiguous()
+    nb = x.shape[0]
+    S = torch.empty((nb, 8), dtype=torch.float32, device=x.device)
+    U = torch.empty((nb, 8, 8), dtype=torch.float32, device=x.device) if vectors else None
+    Vt = torch.empty((nb, 8, 8), dtype=torch.float32, device=x.device) if vectors else None
+    sw = torch.empty((nb,), dtype=torch.int32, device=x.device) if return_sweeps else None
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.tmf_svd8x8_f32(x.data_ptr(), nb, S.data_ptr(), U.data_ptr() if vectors else None,
+                                      Vt.data_ptr() if vectors else None, sw.data_ptr() if return_sweeps else None,
+                                      1 if complete_u else 0, _stream_ptr(torch)))
+    S = S.reshape(*lead, 8)
+    res = (U.reshape(*lead, 8, 8), S, Vt.reshape(*lead, 8, 8)) if vectors else S
+    return (res, sw.reshape(lead)) if return_sweeps else res
+
+
+def dct8x8(blocks, inverse=False):
+    """Batched orthonormal 2-D DCT (or inverse) of CUDA float32 ``(..., 8, 8)`` blocks."""
+    torch = _torch()
+    if not (isinstance(blocks, torch.Tensor) and blocks.is_cuda and blocks.dtype == torch.float32):
+        raise ValueError("blocks must be a CUDA float32 tensor")
+    if blocks.shape[-2:] != (8, 8):
+        raise ValueError("only 8x8 blocks are supported (the reference's BLOCK_SIZE); no CPU fallback")
+    x = blocks.contiguous()
+    out = torch.empty_like(x)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.tmf_dct8x8_f32(x.data_ptr(), out.data_ptr(), x.numel() // 64, 1 if inverse else 0,
+                                      _stream_ptr(torch)))
+    return out
+
+
+# ---------------------------------------------------------------------------
+# the reference's helper names (NumPy / PIL in, NumPy out), computed on the GPU
+# ---------------------------------------------------------------------------
+def rgb_to_ycbcr(img):
+    """watermarking.py:23-50: PIL image or uint8/any-int array (H, W, 3|4) ->
+    float32 (H, W, 3) YCbCr with Cb, Cr offset by 0.5."""
+    torch = _torch()
+    if isinstance(img, Image.Image):
+        img = img.convert("RGB")
+    arr = np.asarray(img)
+    if arr.dtype != np.uint8:
+        raise ValueError("rgb_to_ycbcr takes 8-bit images (the reference feeds it PIL RGB images)")
+    if arr.ndim != 3 or arr.shape[-1] not in (3, 4):
+        raise ValueError(f"expected (H, W, 3) or (H, W, 4), got {arr.shape}")
+    arr = np.ascontiguousarray(arr[:, :, :3])
+    h, w, _ = arr.shape
+    x = torch.from_numpy(arr).cuda()
+    out = torch.empty((h, w, 3), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().tmf_rgb8_to_ycbcr_f32(x.data_ptr(), out.data_ptr(), h * w, _stream_ptr(torch)))
+    return out.cpu().numpy()
+
+
+def ycbcr_to_rgb(img):
+    """watermarking.py:53-73: float32 (H, W, 3) YCbCr -> uint8 (H, W, 3) RGB
+    (clip, then truncating quantiser)."""
+    torch = _torch()
+    arr = np.ascontiguousarray(np.asarray(img, dtype=np.float32))
+    if arr.ndim != 3 or arr.shape[-1] != 3:
+        raise ValueError(f"expected (H, W, 3), got {arr.shape}")
+    h, w, _ = arr.shape
+    x = torch.from_numpy(arr).cuda()
+    out = torch.empty((h, w, 3), dtype=torch.uint8, device=x.device)
+    _lib.check(_lib.load().tmf_ycbcr_f32_to_rgb8(x.data_ptr(), out.data_ptr(), h * w, _stream_ptr(torch)))
+    return out.cpu().numpy()
+
+
+def _block_tap(block, inverse):
+    torch = _torch()
+    arr = np.ascontiguousarray(np.asarray(block, dtype=np.float32))
+    if arr.shape != (8, 8):
+        raise ValueError(f"block_size {arr.shape} is not supported: only the reference's 8x8 blocks "
+                         "(no CPU fallback)")
+    return dct8x8(torch.from_numpy(arr).cuda(), inverse=inverse).cpu().numpy()
+
+
+def apply_dct_to_block(block):
+    """watermarking.py:76-78."""
+    return _block_tap(block, False)
+
+
+def apply_idct_to_block(block):
+    """watermarking.py:81-83."""
+    return _block_tap(block, True)
+
+
+def resize_watermark(watermark, target_height, target_width, preserve_ratio=False):
+    """watermarking.py:86-132 - stays on the host (PIL LANCZOS is the reference's
+    resampler; north_star keeps QR handling on the host).  Bytes or PIL in, PIL
+    "L" image of exactly (target_width, target_height) out; with
+    ``preserve_ratio`` the mark is scaled to fit and centred on white."""
+    img = Image.open(io.BytesIO(watermark)) if isinstance(watermark, bytes) else watermark
+    img = img.convert("L")
+    if not preserve_ratio:
+        return img.resize((target_width, target_height), Image.LANCZOS)
+    src_w, src_h = img.size
+    scale = min(target_width / src_w, target_height / src_h)
+    fit_w, fit_h = int(src_w * scale), int(src_h * scale)
+    fitted = img.resize((fit_w, fit_h), Image.LANCZOS)
+    canvas = Image.new("L", (target_width, target_height), 255)
+    canvas.paste(fitted, ((target_width - fit_w) // 2, (target_height - fit_h) // 2))
+    return canvas
+
+
+# ---------------------------------------------------------------------------
+# the two entry points the pages call
+# ---------------------------------------------------------------------------
+def _require_block8(block_size):
+    if block_size != 8:
+        raise ValueError(f"block_size {block_size} is not supported: this build implements the reference's "
+                         "BLOCK_SIZE = 8 only (there is no CPU fallback)")
+
+
+def embed_watermark(image, watermark_data, preserve_ratio=False, custom_settings=None):
+    """watermarking.py:135-221.  ``image``: PIL image of any mode;
+    ``watermark_data``: PNG bytes or PIL image.  Returns a new PIL "RGB" image of
+    the same size.  Called by ``internal_pages/embed_watermark_page.py:529-531``
+    as ``embed_watermark(img, watermark_data, preserve_ratio=True)``."""
+    torch = _torch()
+    block_size, alpha, mode = _resolve(custom_settings)
+    _require_block8(block_size)
+    image = image.convert("RGB")
+    wm_img = Image.open(io.BytesIO(watermark_data)) if isinstance(watermark_data, bytes) else watermark_data
+    rgb = np.asarray(image)
+    h, w = rgb.shape[:2]
+    wm_map = np.asarray(resize_watermark(wm_img, h // block_size, w // block_size, preserve_ratio))
+    x = torch.from_numpy(np.ascontiguousarray(rgb)).cuda(non_blocking=True)
+    m = torch.from_numpy(np.ascontiguousarray(wm_map)).cuda(non_blocking=True)
+    out = embed_tensor(x, m, alpha, block_size, mode)
+    return Image.fromarray(out.cpu().numpy())
+
+
+def extract_watermark(watermarked_image, original_image, custom_settings=None):
+    """watermarking.py:224-294.  Returns a PIL "L" image of size (W//8, H//8).
+    Called by ``internal_pages/extract_watermark_page.py:293-296``."""
+    torch = _torch()
+    block_size, alpha, mode = _resolve(custom_settings)
+    _require_block8(block_size)
+    a = np.ascontiguousarray(np.asarray(watermarked_image.convert("RGB")))
+    b = np.ascontiguousarray(np.asarray(original_image.convert("RGB")))
+    if a.shape != b.shape:
+        raise ValueError(f"watermarked image {a.shape[1]}x{a.shape[0]} and original image "
+                         f"{b.shape[1]}x{b.shape[0]} must have the same size")
+    out = extract_tensor(torch.from_numpy(a).cuda(non_blocking=True), torch.from_numpy(b).cuda(non_blocking=True),
+                         alpha, block_size, mode)
+    return Image.fromarray(out.cpu().numpy())
+
+
+# ---------------------------------------------------------------------------
+# batch API (the embed page's per-image loop, embed_watermark_page.py:492-558,
+# as one call); host arrays in, host arrays out, by-image sharding over devices
+# ---------------------------------------------------------------------------
+def embed_watermark_batch(images, watermark_map, alpha=ALPHA, block_size=BLOCK_SIZE, mode=None,
+                          devices: Optional[Sequence[int]] = None, out=None):
+    """``images``: uint8 ``(N, H, W, 3)`` NumPy array or (pinned) CPU torch tensor.
+    ``watermark_map``: uint8 ``(H//8, W//8)`` (shared) or ``(N, H//8, W//8)``.
+    Returns uint8 ``(N, H, W, 3)`` of the same kind.  See pipeline.HostPipeline."""
+    from .pipeline import run_batch
+
+    return run_batch("embed", images, None, watermark_map, alpha, block_size, mode, devices, out)
+
+
+def extract_watermark_batch(watermarked, originals, alpha=ALPHA, block_size=BLOCK_SIZE, mode=None,
+                            devices: Optional[Sequence[int]] = None, out=None):
+    """Batched ``extract_watermark``: uint8 ``(N, H, W, 3)`` x2 -> uint8 ``(N, H//8, W//8)``."""
+    from .pipeline import run_batch
+
+    return run_batch("extract", watermarked, originals, None, alpha, block_size, mode, devices, out)

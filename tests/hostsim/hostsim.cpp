@@ -64,12 +64,22 @@ int hostsim_extract(const uint8_t* wmk, const uint8_t* orig, uint8_t* out, int h
   return 0;
 }
 
-static void load_luma255(const uint8_t* rgb, int w, int by, int bx, float* a) {
-  for (int i = 0; i < 8; ++i)
-    for (int j = 0; j < 8; ++j) {
-      const uint8_t* p = rgb + ((size_t)(by * 8 + i) * w + bx * 8 + j) * 3;
-      a[8 * i + j] = luma255_fast((float)p[0], (float)p[1], (float)p[2]);
-    }
+static void row_rgb255(const uint8_t* rgb, int w, int y, int x0, float* r, float* g, float* b) {
+  for (int j = 0; j < 8; ++j) {
+    const uint8_t* p = rgb + ((size_t)y * w + x0 + j) * 3;
+    r[j] = (float)p[0]; g[j] = (float)p[1]; b[j] = (float)p[2];
+  }
+}
+
+static void gram_of_block(const uint8_t* rgb, int w, int by, int bx, float* gm, float* keep = nullptr) {
+  for (int k = 0; k < 36; ++k) gm[k] = 0.0f;
+  for (int i = 0; i < 8; ++i) {
+    float r[8], g[8], b[8], y[8];
+    row_rgb255(rgb, w, by * 8 + i, bx * 8, r, g, b);
+    for (int j = 0; j < 8; ++j) y[j] = luma255_fast(r[j], g[j], b[j]);
+    if (keep) for (int j = 0; j < 8; ++j) keep[8 * i + j] = y[j];
+    gram_accumulate_row(y, gm);
+  }
 }
 
 int hostsim_embed_fast(const uint8_t* rgb, uint8_t* out, int h, int w, const uint8_t* wm, double alpha,
@@ -83,19 +93,23 @@ int hostsim_embed_fast(const uint8_t* rgb, uint8_t* out, int h, int w, const uin
   }
   for (int by = 0; by < nbh; ++by)
     for (int bx = 0; bx < nbw; ++bx) {
-      float a[64];
-      load_luma255(rgb, w, by, bx, a);
-      int sq;
-      float sig = embed_block_fast(a, alpha, wm[by * nbw + bx], &sq);
+      float gm[36], wv[8], f, c, lum[64];
+      gram_of_block(rgb, w, by, bx, gm, lum);
+      int it;
+      float sig = embed_block_scalars_fast(gm, alpha, wm[by * nbw + bx], wv, f, c, &it);
       if (sigma_out) sigma_out[by * nbw + bx] = sig;
-      if (sweeps_out) sweeps_out[by * nbw + bx] = sq;
-      for (int i = 0; i < 8; ++i)
-        for (int j = 0; j < 8; ++j) {
-          size_t p = (size_t)(by * 8 + i) * w + bx * 8 + j;
-          float R, G, B;
-          rgb255_out_fast((float)rgb[3 * p], (float)rgb[3 * p + 1], (float)rgb[3 * p + 2], a[8 * i + j], R, G, B);
-          out[3 * p] = (uint8_t)quant255(R); out[3 * p + 1] = (uint8_t)quant255(G); out[3 * p + 2] = (uint8_t)quant255(B);
+      if (sweeps_out) sweeps_out[by * nbw + bx] = it;
+      for (int i = 0; i < 8; ++i) {
+        float r[8], g[8], b[8];
+        int q[24];
+        row_rgb255(rgb, w, by * 8 + i, bx * 8, r, g, b);
+        embed_row_fast(r, g, b, lum + 8 * i, wv, f, c, q);
+        uint8_t* dst = out + ((size_t)(by * 8 + i) * w + bx * 8) * 3;
+        for (int k = 0; k < 6; ++k) {
+          uint32_t word = pack4_sat_u8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
+          for (int t = 0; t < 4; ++t) dst[4 * k + t] = (uint8_t)(word >> (8 * t));
         }
+      }
     }
   return 0;
 }
@@ -104,11 +118,11 @@ int hostsim_extract_fast(const uint8_t* wmk, const uint8_t* orig, uint8_t* out, 
   const int nbh = h / 8, nbw = w / 8;
   for (int by = 0; by < nbh; ++by)
     for (int bx = 0; bx < nbw; ++bx) {
-      float a[64];
-      load_luma255(wmk, w, by, bx, a);
-      float sw = sigma0_block_fast(a, nullptr);
-      load_luma255(orig, w, by, bx, a);
-      float so = sigma0_block_fast(a, nullptr);
+      float gm[36];
+      gram_of_block(wmk, w, by, bx, gm);
+      float sw = sigma0_from_gram_fast(gm, nullptr);
+      gram_of_block(orig, w, by, bx, gm);
+      float so = sigma0_from_gram_fast(gm, nullptr);
       out[by * nbw + bx] = (uint8_t)extract_level(sw, so, alpha);
     }
   return 0;

@@ -9,14 +9,15 @@ import numpy as np
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
 SO = os.path.join(HERE, "_hostsim.so")
 SRC = os.path.join(HERE, "hostsim.cpp")
-HDR = os.path.join(os.path.dirname(HERE), "..", "thatsmyface_b200", "csrc", "tmf_math.cuh")
+CSRC = os.path.join(os.path.dirname(HERE), "..", "thatsmyface_b200", "csrc")
+HDRS = [os.path.join(CSRC, "tmf_math.cuh"), os.path.join(CSRC, "tmf_fast.cuh")]
 _lib = None
 
 
 def lib():
     global _lib
     if _lib is None:
-        stale = (not os.path.exists(SO)) or any(os.path.getmtime(p) > os.path.getmtime(SO) for p in (SRC, HDR))
+        stale = (not os.path.exists(SO)) or any(os.path.getmtime(p) > os.path.getmtime(SO) for p in [SRC] + HDRS)
         if stale:
             subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", SRC, "-o", SO, "-lm"],
                            check=True)

@@ -34,12 +34,13 @@ _lib = None
 def load() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(LIBPATH):
+        path = os.environ.get("TMF_LIBPATH", LIBPATH)   # tuning sweeps load alternative builds of the same source
+        if not os.path.exists(path):
             raise RuntimeError(
-                f"{LIBPATH} is missing: build it with `python -m thatsmyface_b200.build` "
+                f"{path} is missing: build it with `python -m thatsmyface_b200.build` "
                 "(nvcc, sm_100a).  There is no CPU fallback for the watermark path."
             )
-        lib = C.CDLL(LIBPATH)
+        lib = C.CDLL(path)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(lib, name)  # AttributeError if the .so does not export it
             fn.restype, fn.argtypes = res, args

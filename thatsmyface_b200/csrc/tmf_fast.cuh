@@ -1,50 +1,59 @@
-// FAST mode: algebraically reduced embed / extract of one 8x8 luma block.
+// FAST mode: algebraically reduced embed / extract of one 8x8 luma block,
+// organised as two streaming passes over the block's rows.
 //
-// The orthonormal 2-D DCT preserves singular values, and for D = C B C^T with
-// D = U S V^T the reference's output block is
-//     IDCT(U diag(S + d e0) V^T) = B + d * (C^T u0)(C^T v0)^T = B + d * u0_B v0_B^T
+// Algebra.  The orthonormal 2-D DCT preserves singular values, and for
+// D = C B C^T with D = U S V^T the reference's output block is
+//     IDCT(U diag(S + d e0) V^T) = B + d (C^T u0)(C^T v0)^T = B + d u0_B v0_B^T
 // (modules/watermarking.py:192-204), where (s0, u0_B, v0_B) is the top singular
-// triplet of the *spatial* block B.  So embed needs one singular triplet and a
-// rank-1 update, extract needs one singular value; no DCT, no full SVD.
+// triplet of the *spatial* block B.  Embed needs one triplet and a rank-1
+// update, extract needs one singular value; no DCT, no full SVD.
 //
-// Top triplet, robustly: G = B^T B (symmetric PSD, 36 unique entries), scaled
-// to unit trace, then repeated squaring P = M*M.  With tr(M) = 1,
-//     1 - tr(P) = sum_i mu_i (1 - mu_i) >= mu_1/mu_0-ish
-// is a rigorous (up to rounding) bound on how far M is from rank one, whatever
-// the spectral gap, and every squaring squares the eigenvalue ratios.  When the
-// bound is met, the column of P with the largest diagonal entry is v0 to
-// ~(bound/2)^2; sigma0 = ||B v0|| (a Rayleigh quotient: second-order accurate)
-// and u0 = B v0 / sigma0.
+// Streaming.  Nothing below ever holds the 64 luma values of a block.
+//   pass 1 (per row):  luma of the row -> G += row^T row      (G = B^T B, 36 regs);
+//                      the row's luma is parked in a thread-private shared-memory column
+//   middle:            top eigenpair (mu, w) of M = G / tr(G)
+//   pass 2 (per row):  z = row.w, d_j = f z w_j with f = d255 / (sigma255 w.w),
+//                      pixel out = M_rgb k + d_j, clip, truncate
+// so the row loops stay rolled (small code: the unrolled version stalled on
+// instruction fetch, profiles/r01_*) and the register file holds G, not B.
+//
+// Top eigenpair, robustly.  B >= 0 (luma) makes G >= 0 entrywise, so by
+// Perron-Frobenius v0 >= 0 and the all-ones start has tan(angle to v0) <= sqrt 7.
+// M has unit trace, so for any x the Rayleigh quotient mu^ <= mu_0 gives
+//     rho^ = (1 - mu^) / mu^ >= (sum_{i>=1} mu_i) / mu_0 >= mu_1 / mu_0:
+// a certified upper bound on the power-iteration ratio that needs no knowledge
+// of the gap.  After J products w_J = M^J 1 the vector error is <= sqrt7 rho^^J
+// and mu~ = (w_J.w_J)/(w_{J-1}.w_J) <= mu_0 is off by <= 7 rho^^(2J-1); J <= 5 is
+// read off precomputed thresholds.  Blocks whose bound is too weak for that
+// (textured, near-tied) take the slow path: repeated squaring P = M M, where
+// 1 - tr(P) bounds the distance from rank one for any gap.
 //
 // Pixels are carried in 0..255 units (exact small integers as floats); colour
-// math is fp32 FMA with the reference's constants folded - accurate to ~2 ulp
-// of the reference's float64-dot-then-float32 values, not bit-identical (the
-// faithful mode is).  All of it is CUDA-core fp32: the contractions are 8 wide.
+// math is fp32 FMA with the reference's constants - within ~2 ulp of the
+// reference's float64-dot-then-float32 values, not bit-identical (the faithful
+// mode is).  All CUDA-core fp32: every contraction here is 8 wide.
 #pragma once
 #include "tmf_math.cuh"
 
 namespace tmf {
 
-// embed must resolve u0 v0^T to ~1e-6; extract only needs sigma0, whose error is
-// second order in the vector error, so it can stop a squaring earlier.
-#define TMF_FAST_TOL_EMBED 2.0e-3f
-#define TMF_FAST_TOL_EXTRACT 3.0e-2f
+#define TMF_FAST_TOL_EMBED 2.0e-3f     // slow path: 1 - tr(P) at which P's top column is v0 to ~1e-6
+#define TMF_FAST_TOL_EXTRACT 3.0e-2f   // extract needs sigma0 only (second order in the vector error)
 #define TMF_FAST_MAX_SQUARINGS 18
 
 // upper triangle of a symmetric 8x8 in 36 registers: index of (i, j), i <= j
 #define TMF_SYM(i, j) ((i) * 8 - ((i) * ((i) + 1)) / 2 + (j))
+#define TMF_SYMG(m, i, j) ((m)[((i) <= (j)) ? TMF_SYM(i, j) : TMF_SYM(j, i)])
 
-// g = B^T B (upper triangle); returns trace
-TMF_HD float gram_upper(const float* b, float* g) {
+// pass 1: G += y^T y for one row y[8] of the block
+TMF_HD void gram_accumulate_row(const float* y, float* g) {
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = i; j < 8; ++j) {
-      float s = 0.f;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) s = fmaf(b[8 * r + i], b[8 * r + j], s);
-      g[TMF_SYM(i, j)] = s;
-    }
+    for (int j = i; j < 8; ++j) g[TMF_SYM(i, j)] = fmaf(y[i], y[j], g[TMF_SYM(i, j)]);
+}
+
+TMF_HD float sym_trace(const float* g) {
   float tr = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) tr += g[TMF_SYM(i, i)];
@@ -59,34 +68,44 @@ TMF_HD float sym_square(const float* m, float* p) {
     for (int j = i; j < 8; ++j) {
       float s = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float a = m[(i <= k) ? TMF_SYM(i, k) : TMF_SYM(k, i)];
-        const float c = m[(k <= j) ? TMF_SYM(k, j) : TMF_SYM(j, k)];
-        s = fmaf(a, c, s);
-      }
+      for (int k = 0; k < 8; ++k) s = fmaf(TMF_SYMG(m, i, k), TMF_SYMG(m, k, j), s);
       p[TMF_SYM(i, j)] = s;
     }
-  float tr = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) tr += p[TMF_SYM(i, i)];
-  return tr;
+  return sym_trace(p);
 }
 
-// Top right-singular vector of B (unit norm) from its Gram matrix by repeated
-// squaring.  g is destroyed.  Returns the number of squarings.  tr must be > 0.
-TMF_HD int top_eigvec_by_squaring(float* g, float tr, float tol, float* v) {
-  float p[36];
-  float inv = f_rcp_fast(tr);
+// y = M x for symmetric M (upper triangle)
+TMF_HD void sym_matvec(const float* m, const float* x, float* y) {
 #pragma unroll
-  for (int k = 0; k < 36; ++k) g[k] *= inv;
+  for (int i = 0; i < 8; ++i) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s = fmaf(TMF_SYMG(m, i, j), x[j], s);
+    y[i] = s;
+  }
+}
+
+TMF_HD float dot8(const float* a, const float* b) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s = fmaf(a[i], b[i], s);
+  return s;
+}
+
+// Slow path: repeated squaring of a copy of the unit-trace M; rigorous for any
+// spectral gap.  w = unit top eigenvector, mu = w.Mw.  Returns the squarings.
+TMF_HD int top_pair_by_squaring(const float* m, float tol, float* w, float& ww, float& mu) {
+  float q[36], p[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) q[k] = m[k];
   int it = 0;
   for (;;) {
-    const float t = sym_square(g, p);     // tr(g) == 1, so t = sum mu_i^2
+    const float t = sym_square(q, p);     // tr(q) == 1, so t = sum of squared eigenvalue shares
     ++it;
     if (1.0f - t <= tol || it >= TMF_FAST_MAX_SQUARINGS) break;
-    inv = f_rcp_fast(t);
+    const float inv = f_rcp_fast(t);
 #pragma unroll
-    for (int k = 0; k < 36; ++k) g[k] = p[k] * inv;
+    for (int k = 0; k < 36; ++k) q[k] = p[k] * inv;
   }
   // column of p with the largest diagonal entry (>= 1/8 of the trace)
   float best = p[TMF_SYM(0, 0)];
@@ -96,85 +115,111 @@ TMF_HD int top_eigvec_by_squaring(float* g, float tr, float tol, float* v) {
     const float d = p[TMF_SYM(j, j)];
     if (d > best) { best = d; col = j; }
   }
-  float n2 = 0.f;
+  float y[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float x = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float e = p[(i <= j) ? TMF_SYM(i, j) : TMF_SYM(j, i)];
-      x = (j == col) ? e : x;
-    }
-    v[i] = x;
-    n2 = fmaf(x, x, n2);
+    for (int j = 0; j < 8; ++j) x = (j == col) ? TMF_SYMG(p, i, j) : x;
+    y[i] = x;
   }
+  const float n2 = dot8(y, y);
   float rn = f_rsqrt(n2);
   rn = fmaf(0.5f * rn, fmaf(-n2 * rn, rn, 1.0f), rn);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] *= rn;
+  for (int i = 0; i < 8; ++i) w[i] = y[i] * rn;
+  float mw[8];
+  sym_matvec(m, w, mw);
+  ww = dot8(w, w);
+  mu = dot8(w, mw) * f_rcp_fast(ww);
   return it;
 }
 
-// sigma0 and (optionally) u0 = B v0 / sigma0 from a unit v0
-template <bool WITH_U>
-TMF_HD float sigma_from_v(const float* b, const float* v, float* u) {
-  float z[8], n2 = 0.f;
+// Top eigenpair of the unit-trace Gram matrix m (entrywise >= 0) of a luma block.
+// On return w (NOT normalised, ww = w.w) spans v0 and mu ~ mu_0 (relative 1e-7).
+// Returns the number of M products (fast path) or 100 + squarings (slow path).
+template <bool EMBED>
+TMF_HD int top_pair(const float* m, float* w, float& ww, float& mu) {
+  float x[8], y[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 8; ++i) {          // x = M 1
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s = fmaf(b[8 * i + j], v[j], s);
-    z[i] = s;
-    n2 = fmaf(s, s, n2);
+    for (int j = 0; j < 8; ++j) s += TMF_SYMG(m, i, j);
+    x[i] = s;
   }
-  const float sig = f_sqrt(n2);
-  if (WITH_U) {
-    const float inv = f_div(1.0f, sig);
+  sym_matvec(m, x, y);                   // y = M^2 1
+  float xx = dot8(x, x), xy = dot8(x, y), yy = dot8(y, y);
+  const float rho = fmaxf(xx - xy, 0.0f) * f_rcp_fast(xy);
+  // embed: sqrt7 rho^J <= 1e-6 (u0 v0^T itself);  extract: 7 rho^(2J-1) <= 1e-7 (sigma0 only)
+  const float r2 = EMBED ? 6.1e-4f : 2.4e-3f;
+  const float r3 = EMBED ? 7.2e-3f : 2.7e-2f;
+  const float r4 = EMBED ? 2.48e-2f : 7.5e-2f;
+  const float r5 = EMBED ? 5.2e-2f : 1.34e-1f;
+  if (rho <= r5) {
+    const int more = (rho <= r2) ? 0 : (rho <= r3) ? 1 : (rho <= r4) ? 2 : 3;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) u[i] = z[i] * inv;
+    for (int k = 0; k < 3; ++k) {
+      if (k < more) {
+        sym_matvec(m, y, x);             // x = M y
+        xy = dot8(y, x);                 // w_{J-1}.w_J
+        yy = dot8(x, x);                 // w_J.w_J
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = x[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = y[i];
+    ww = yy;
+    mu = yy * f_rcp_fast(xy);
+    return 2 + more;
   }
-  return sig;
+  return 100 + top_pair_by_squaring(m, EMBED ? TMF_FAST_TOL_EMBED : TMF_FAST_TOL_EXTRACT, w, ww, mu);
 }
 
-// Largest singular value of a spatial luma block given in 0..255 units; result
-// in the reference's units (luma in [0, 1]).
-TMF_HD float sigma0_block_fast(const float* b255, int* squarings) {
-  float g[36], v[8];
-  const float tr = gram_upper(b255, g);
-  if (squarings) *squarings = 0;
-  if (!(tr > 0.0f)) return 0.0f;
-  const int it = top_eigvec_by_squaring(g, tr, TMF_FAST_TOL_EXTRACT, v);
-  if (squarings) *squarings = it;
-  return sigma_from_v<false>(b255, v, nullptr) * (1.0f / 255.0f);
-}
-
-// Embed on a spatial luma block in 0..255 units, in place: b += d255 * u0 v0^T,
-// d255 = 255 * (f32(f64(s0) + alpha*w) - s0)   (watermarking.py:198).
-// Returns sigma0 in the reference's units.
-TMF_HD float embed_block_fast(float* b255, double alpha, uint32_t wm_u8, int* squarings) {
-  float g[36], v[8], u[8];
-  const float tr = gram_upper(b255, g);
-  float sig = 0.0f;
+// Per-block scalars of the embed, from the Gram matrix accumulated in pass 1
+// (g in 0..255 units, destroyed).  Output for pass 2:
+//   w[8], and  y'_ij = y_ij + (f * z_i + c) * w_j,  z_i = row_i . w
+// with (f, c) = (d255 / (sigma255 w.w), 0), or (0, d255/8) with w = 1 for an
+// all-zero block (LAPACK's U = V = I puts the mark on the DC coefficient, which
+// is the constant 1/8 pattern in the spatial domain).  Returns sigma0 in the
+// reference's units (luma in [0, 1]).
+TMF_HD float embed_block_scalars_fast(float* g, double alpha, uint32_t wm_u8, float* w, float& f, float& c,
+                                      int* iters) {
+  const float tr = sym_trace(g);
+  float sig255 = 0.0f, ww = 8.0f;
   if (tr > 0.0f) {
-    const int it = top_eigvec_by_squaring(g, tr, TMF_FAST_TOL_EMBED, v);
-    if (squarings) *squarings = it;
-    sig = sigma_from_v<true>(b255, v, u) * (1.0f / 255.0f);
+    const float inv = f_rcp_fast(tr);
+#pragma unroll
+    for (int k = 0; k < 36; ++k) g[k] *= inv;
+    float mu;
+    const int it = top_pair<true>(g, w, ww, mu);
+    if (iters) *iters = it;
+    sig255 = f_sqrt(tr * mu);
   } else {
-    // all-zero block: LAPACK returns U = V = I in the DCT domain, i.e. the DC
-    // basis function, which is the constant 1/sqrt(8) vector in the spatial domain
-    if (squarings) *squarings = 0;
+    if (iters) *iters = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { u[i] = TMF_G0; v[i] = TMF_G0; }
+    for (int i = 0; i < 8; ++i) w[i] = 1.0f;
   }
-  const float sig_new = modulate_sigma0(sig, alpha, wm_u8);
-  const float d255 = (sig_new - sig) * 255.0f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float du = d255 * u[i];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) b255[8 * i + j] = fmaf(du, v[j], b255[8 * i + j]);
-  }
+  const float sig = sig255 * (1.0f / 255.0f);
+  const float d255 = (modulate_sigma0(sig, alpha, wm_u8) - sig) * 255.0f;   // watermarking.py:198
+  if (tr > 0.0f) { f = f_div(d255, sig255 * ww); c = 0.0f; }
+  else { f = 0.0f; c = d255 * 0.125f; }
   return sig;
+}
+
+// Largest singular value (reference units) from the pass-1 Gram matrix (destroyed).
+TMF_HD float sigma0_from_gram_fast(float* g, int* iters) {
+  const float tr = sym_trace(g);
+  if (iters) *iters = 0;
+  if (!(tr > 0.0f)) return 0.0f;
+  const float inv = f_rcp_fast(tr);
+#pragma unroll
+  for (int k = 0; k < 36; ++k) g[k] *= inv;
+  float w[8], ww, mu;
+  const int it = top_pair<false>(g, w, ww, mu);
+  if (iters) *iters = it;
+  return f_sqrt(tr * mu) * (1.0f / 255.0f);
 }
 
 // --- fp32 colour in 0..255 units -------------------------------------------
@@ -183,20 +228,56 @@ TMF_HD float luma255_fast(float r, float g, float b) {
   return fmaf(0.299f, r, fmaf(0.587f, g, 0.114f * b));
 }
 // watermarking.py:37-48 and :58-73 composed: the reference maps (r, g, b) to
-// (y, cb, cr), replaces y by y', and maps back with a matrix that is not the
-// exact inverse.  out_c = y' + k_c . (cb, cr), all in 0..255 units, then clip
-// and truncate.  `dy` = y' - y.
-TMF_HD void rgb255_out_fast(float r, float g, float b, float y_new, float& R, float& G, float& B) {
-  const float cb = fmaf(-0.169f, r, fmaf(-0.331f, g, 0.5f * b));
-  const float cr = fmaf(0.5f, r, fmaf(-0.419f, g, -0.081f * b));
-  R = fmaf(1.403f, cr, y_new);
-  G = fmaf(-0.714f, cr, fmaf(-0.344f, cb, y_new));
-  B = fmaf(1.773f, cb, y_new);
+// (y, cb, cr), adds the mark to y, and maps back with a matrix that is not the
+// exact inverse, so a pixel comes back as  M k + d  with  M = Ti T  (the two
+// reference matrices multiplied out in float64) and d the luma change of that
+// pixel.  All in 0..255 units; the caller clips and truncates.
+TMF_HD void rgb255_out_fast(float r, float g, float b, float d, float& R, float& G, float& B) {
+  R = fmaf(1.0005f, r, fmaf(-8.57e-4f, g, fmaf(3.57e-4f, b, d)));
+  G = fmaf(1.36e-4f, r, fmaf(1.00003f, g, fmaf(-1.66e-4f, b, d)));
+  B = fmaf(-6.37e-4f, r, fmaf(1.37e-4f, g, fmaf(1.0005f, b, d)));
 }
-// clip [0, 255] and truncate toward zero (values are >= 0 after the clip)
-TMF_HD uint32_t quant255(float x) {
-  x = fminf(fmaxf(x, 0.0f), 255.0f);
-  return (uint32_t)x;
+
+// floor(x) as a signed integer for |x| < 2^22 with one FADD.RM (round toward
+// -inf into the mantissa of 1.5*2^23) and one integer subtract - both full-rate
+// pipes, unlike F2I (measured 16/clk/SM on B200, profiles/r01_ubench.txt).
+// The clip to [0, 255] (watermarking.py:70) is done by the packing instruction;
+// for the clipped value floor == the reference's truncation (:73).
+TMF_HD int floor_to_int(float x) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(__fadd_rd(x, 12582912.0f)) - 0x4B400000;
+#else
+  return (int)floorf(x);
+#endif
+}
+
+// four floors -> four saturated bytes in one word (byte 0 = a0): two
+// cvt.pack.sat.u8.s32 (SASS I2IP.U8.S32.SAT), each clamps and packs two values.
+TMF_HD uint32_t pack4_sat_u8(int a0, int a1, int a2, int a3) {
+#if defined(__CUDA_ARCH__)
+  uint32_t hi, w;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(a3), "r"(a2), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(a1), "r"(a0), "r"(hi));
+  return w;
+#else
+  auto cl = [](int v) { return (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); };
+  return cl(a0) | (cl(a1) << 8) | (cl(a2) << 16) | (cl(a3) << 24);
+#endif
+}
+
+// pass 2 for one row: r, g, b in 0..255 units and the row's luma y (kept from
+// pass 1) -> 24 output levels q[3j + c] (unclipped floors; pack4_sat_u8 clips)
+TMF_HD void embed_row_fast(const float* r, const float* g, const float* b, const float* y, const float* w, float f,
+                           float c, int* q) {
+  const float du = fmaf(f, dot8(y, w), c);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float R, G, B;
+    rgb255_out_fast(r[j], g[j], b[j], du * w[j], R, G, B);
+    q[3 * j] = floor_to_int(R);
+    q[3 * j + 1] = floor_to_int(G);
+    q[3 * j + 2] = floor_to_int(B);
+  }
 }
 
 }  // namespace tmf

@@ -112,8 +112,17 @@ TMF_HD float dot3_npdot(double t0, double t1, double t2, float x0, float x1, flo
   return (float)acc;
 }
 
-// watermarking.py:29 - f32(u8) / 255.0 (IEEE float32 division)
-TMF_HD float unit_from_u8(uint32_t v) { return f_div((float)v, 255.0f); }
+// watermarking.py:29 - f32(u8) / 255.0 (IEEE float32 division).  For the 256
+// possible inputs the quotient is reproduced exactly by one FMA-corrected
+// reciprocal step (checked for every byte by tests/test_hostsim.py and by the
+// bit-exact colour taps), which avoids the ~12-instruction division sequence.
+TMF_HD float unit_from_u8(uint32_t v) {
+  const float k = (float)v;
+  const float r = 0.00392156885936856270f;        // RN32(1/255)
+  const float q0 = f_mul(k, r);
+  const float e = fmaf(-q0, 255.0f, k);           // exact residual
+  return fmaf(e, r, q0);
+}
 
 // watermarking.py:37-48 (Y only)
 TMF_HD float luma_exact(float r, float g, float b) {
@@ -244,56 +253,77 @@ TMF_HD float pow2_scale_for(float frob2, float& unscale) {
 #endif
 }
 
-template <bool WITH_V, int P, int Q>
-TMF_HD bool jacobi_pair(float* a, float* v) {
-  float al = 0.f, be = 0.f, ga = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    al = fmaf(a[8 * i + P], a[8 * i + P], al);
-    be = fmaf(a[8 * i + Q], a[8 * i + Q], be);
-    ga = fmaf(a[8 * i + P], a[8 * i + Q], ga);
-  }
-  const float lim = TMF_JACOBI_TOL * f_sqrt_fast(al * be);
-  const bool rot = (fabsf(ga) > lim) && (fminf(al, be) > TMF_JACOBI_FLOOR);
-  if (rot) {
-    // tan of the rotation angle, smaller root: t = 2g / (d + sign(d) sqrt(d^2 + 4g^2))
-    const float d = be - al, g2 = ga + ga;
-    const float r = f_sqrt_fast(fmaf(g2, g2, d * d));
-    const float t = g2 * f_rcp_fast(d + copysignf(r, d));
-    const float tt = fmaf(t, t, 1.0f);
-    float c = f_rsqrt(tt);
-    c = fmaf(0.5f * c, fmaf(-tt * c, c, 1.0f), c);   // one Newton step: c^2 + s^2 = 1 to ~1 ulp
-    const float s = c * t;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float x = a[8 * i + P], y = a[8 * i + Q];
-      a[8 * i + P] = fmaf(c, x, -s * y);
-      a[8 * i + Q] = fmaf(s, x, c * y);
-    }
-    if (WITH_V) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float x = v[8 * i + P], y = v[8 * i + Q];
-        v[8 * i + P] = fmaf(c, x, -s * y);
-        v[8 * i + Q] = fmaf(s, x, c * y);
-      }
-    }
-  }
-  return rot;
+// Rotation of one column pair from its Gram entries (al, be, ga).  Returns the
+// |cosine| between the two columns if the pair is rotated (c, s set), else 0
+// with (c, s) = (1, 0).  Branch-free: every lane runs the same instructions.
+TMF_HD float jacobi_cs(float al, float be, float ga, float& c, float& s) {
+  const float ab = al * be;
+  const float rab = f_rsqrt(ab);                       // inf when ab == 0 (then rot is false)
+  const float cosv = fabsf(ga) * rab;
+  const bool rot = (cosv > TMF_JACOBI_TOL) && (fminf(al, be) > TMF_JACOBI_FLOOR);
+  // tan of the rotation angle, smaller root: t = 2g / (d + sign(d) sqrt(d^2 + 4g^2))
+  const float d = be - al, g2 = ga + ga;
+  const float r = f_sqrt_fast(fmaf(g2, g2, d * d));
+  const float t = g2 * f_rcp_fast(d + copysignf(r, d));
+  const float tt = fmaf(t, t, 1.0f);
+  float cc = f_rsqrt(tt);
+  cc = fmaf(0.5f * cc, fmaf(-tt * cc, cc, 1.0f), cc);  // one Newton step: c^2 + s^2 = 1 to ~1 ulp
+  c = rot ? cc : 1.0f;
+  s = rot ? cc * t : 0.0f;
+  return rot ? cosv : 0.0f;
 }
 
-template <bool WITH_V, int P, int Q>
-struct JacobiSweep {
-  static TMF_HD bool run(float* a, float* v) {
-    bool r = jacobi_pair<WITH_V, P, Q>(a, v);
-    bool rest = JacobiSweep<WITH_V, (Q == 7 ? P + 1 : P), (Q == 7 ? P + 2 : Q + 1)>::run(a, v);
-    return r || rest;
+// Round-robin ("chess tournament") ordering.  A round rotates the disjoint
+// pairs (0,1) (2,3) (4,5) (6,7); the rotated columns are then written back to
+// the permuted positions PI, so that after 7 rounds every one of the 28 pairs
+// has met once and the columns are back in their original places.  The
+// permutation costs nothing (the rotation outputs simply land in other
+// registers) and it makes every round the SAME code, so a sweep is a rolled
+// loop of 7 iterations: ~8 KB of instructions instead of the ~50 KB of a fully
+// unrolled cyclic sweep, which stalled on instruction fetch (profiles/r01_*).
+//   PI: 0->0 1->2 2->4 3->1 4->6 5->3 6->7 7->5
+#define TMF_PI(p) ((p) == 0 ? 0 : (p) == 1 ? 2 : (p) == 2 ? 4 : (p) == 3 ? 1 : (p) == 4 ? 6 : (p) == 5 ? 3 : (p) == 6 ? 7 : 5)
+
+TMF_HD void rr_apply_rows(float* m, const float* c, const float* s) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = m[8 * i + j];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float x = t[2 * k], y = t[2 * k + 1];
+      m[8 * i + TMF_PI(2 * k)] = fmaf(c[k], x, -s[k] * y);
+      m[8 * i + TMF_PI(2 * k + 1)] = fmaf(s[k], x, c[k] * y);
+    }
   }
-};
+}
+
+// one round; returns the largest |cosine| among the pairs it rotated
 template <bool WITH_V>
-struct JacobiSweep<WITH_V, 7, 8> {
-  static TMF_HD bool run(float*, float*) { return false; }
-};
+TMF_HD float jacobi_round(float* a, float* v) {
+  float c[4], s[4], worst = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float al = 0.f, be = 0.f, ga = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      al = fmaf(a[8 * i + 2 * k], a[8 * i + 2 * k], al);
+      be = fmaf(a[8 * i + 2 * k + 1], a[8 * i + 2 * k + 1], be);
+      ga = fmaf(a[8 * i + 2 * k], a[8 * i + 2 * k + 1], ga);
+    }
+    worst = fmaxf(worst, jacobi_cs(al, be, ga, c[k], s[k]));
+  }
+  rr_apply_rows(a, c, s);
+  if (WITH_V) rr_apply_rows(v, c, s);
+  return worst;
+}
+
+// Sweeps stop when the largest cosine met during a sweep is below
+// TMF_JACOBI_DONE: Jacobi converges quadratically, so the sweep that just ran
+// leaves cosines of order DONE^2 - no extra sweep is spent only to find out
+// that nothing rotates.
+#define TMF_JACOBI_DONE 3.0e-4f
 
 template <bool WITH_V>
 TMF_HD int jacobi_svd8(float* a, float* v, float& unscale) {
@@ -315,8 +345,13 @@ TMF_HD int jacobi_svd8(float* a, float* v, float& unscale) {
   int sweeps = 0;
   bool more = live;
   for (int it = 0; it < TMF_JACOBI_MAX_SWEEPS && more; ++it) {
-    more = JacobiSweep<WITH_V, 0, 1>::run(a, v);
-    sweeps += more ? 1 : 0;
+    float worst = 0.0f;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int r = 0; r < 7; ++r) worst = fmaxf(worst, jacobi_round<WITH_V>(a, v));
+    sweeps += (worst > 0.0f) ? 1 : 0;
+    more = worst > TMF_JACOBI_DONE;
   }
   return sweeps;
 }

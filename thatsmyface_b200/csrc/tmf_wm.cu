@@ -36,6 +36,15 @@ int check_launch(const char* what) {
 
 constexpr int kThreads = 128;
 
+// tunables of the fast kernels (profiles/sweep_variants.py builds and times the alternatives)
+#ifndef TMF_ROW_UNROLL
+#define TMF_ROW_UNROLL 1      // rows per iteration of the rolled row loops (1, 2, 4)
+#endif
+#ifndef TMF_FAST_MIN_CTAS
+#define TMF_FAST_MIN_CTAS 6   // __launch_bounds__ minimum CTAs/SM of the fast kernels
+#endif
+constexpr int kRowUnroll = TMF_ROW_UNROLL;
+
 // ---------------------------------------------------------------------------
 // 24-byte block-row load/store with the widest access the alignment allows
 // ---------------------------------------------------------------------------
@@ -92,9 +101,23 @@ __device__ __forceinline__ size_t block_origin(const BlockGeom& g, long long gb,
   return (size_t)img * g.img_stride + (size_t)by * 8 * g.row_pitch + (size_t)bx * 24;
 }
 
-template <int VEC>
-__device__ __forceinline__ void load_luma_block(const uint8_t* __restrict__ base, size_t pitch, float* a) {
+// Ask for all 8 rows of a block up front.  The row loops below are rolled (small
+// code), so without this each warp would have only one row (3 loads) in flight.
+__device__ __forceinline__ void prefetch_block_rows(const uint8_t* __restrict__ base, size_t pitch) {
 #pragma unroll
+  for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)i * pitch));
+}
+
+// Faithful-mode block I/O.  The DCT / Jacobi need the whole block in registers
+// with compile-time indices, but the per-pixel colour code is long (float64
+// dots, exact division), so unrolling it over 64 pixels made the kernel 230 KB
+// of instructions and it stalled on instruction fetch (profiles/r01_*).  The row
+// loops are therefore rolled and exchange the block with the register file
+// through a thread-private column of shared memory: sm[k * kThreads + tid]
+// (conflict-free, no barrier needed).
+template <int VEC>
+__device__ __forceinline__ void luma_rows_to_smem(const uint8_t* __restrict__ base, size_t pitch, float* __restrict__ col) {
+#pragma unroll 1
   for (int i = 0; i < 8; ++i) {
     uint32_t w[6];
     load_row24<VEC>(base + (size_t)i * pitch, w);
@@ -103,32 +126,45 @@ __device__ __forceinline__ void load_luma_block(const uint8_t* __restrict__ base
       const float r = tmf::unit_from_u8(TMF_BYTE(w, 3 * j));
       const float g = tmf::unit_from_u8(TMF_BYTE(w, 3 * j + 1));
       const float b = tmf::unit_from_u8(TMF_BYTE(w, 3 * j + 2));
-      a[8 * i + j] = tmf::luma_exact(r, g, b);
+      col[(8 * i + j) * kThreads] = tmf::luma_exact(r, g, b);
     }
   }
+}
+
+template <int VEC>
+__device__ __forceinline__ void load_luma_block(const uint8_t* __restrict__ base, size_t pitch, float* __restrict__ col,
+                                                float* a) {
+  luma_rows_to_smem<VEC>(base, pitch, col);
+#pragma unroll
+  for (int k = 0; k < 64; ++k) a[k] = col[k * kThreads];
 }
 
 // ---------------------------------------------------------------------------
 // fused embed, faithful mode (watermarking.py:163-219 in one launch)
 // ---------------------------------------------------------------------------
 template <int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 k_embed_faithful(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGeom g,
                  const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
+  __shared__ float sm[64 * kThreads];
   const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (gb >= g.total_blocks) return;
   long long img; int by, bx;
   const size_t org = block_origin(g, gb, img, by, bx);
   const uint8_t* src = rgb + org;
+  float* col = sm + threadIdx.x;
+  prefetch_block_rows(src, g.row_pitch);
 
   float a[64], v[64];
-  load_luma_block<VEC>(src, g.row_pitch, a);
+  load_luma_block<VEC>(src, g.row_pitch, col, a);
   const long long wi = (wm_shared ? 0 : img * g.blocks_per_img) + (long long)by * g.nbw + bx;
   tmf::embed_block_faithful(a, v, alpha, (uint32_t)__ldg(wm + wi), nullptr);
+#pragma unroll
+  for (int k = 0; k < 64; ++k) col[k * kThreads] = a[k];
 
   // colour out: chroma is recomputed from the (L1/L2-resident) input bytes
   uint8_t* dst = out + org;
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < 8; ++i) {
     uint32_t w[6], o[6] = {0, 0, 0, 0, 0, 0};
     load_row24<VEC>(src + (size_t)i * g.row_pitch, w);
@@ -140,7 +176,7 @@ k_embed_faithful(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, Blo
       float cb, cr;
       tmf::chroma_exact(r, gg, b, cb, cr);
       uint32_t R, G, B;
-      tmf::ycc_to_rgb8_exact(a[8 * i + j], cb, cr, R, G, B);
+      tmf::ycc_to_rgb8_exact(col[(8 * i + j) * kThreads], cb, cr, R, G, B);
       o[(3 * j) >> 2] |= R << (8 * ((3 * j) & 3));
       o[(3 * j + 1) >> 2] |= G << (8 * ((3 * j + 1) & 3));
       o[(3 * j + 2) >> 2] |= B << (8 * ((3 * j + 2) & 3));
@@ -189,10 +225,14 @@ k_extract_faithful(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ 
   if (gb >= g.total_blocks) return;
   long long img; int by, bx;
   const size_t org = block_origin(g, gb, img, by, bx);
+  __shared__ float sm[64 * kThreads];
+  float* col = sm + threadIdx.x;
+  prefetch_block_rows(wmk + org, g.row_pitch);
+  prefetch_block_rows(orig + org, g.row_pitch);
   float a[64];
-  load_luma_block<VEC>(wmk + org, g.row_pitch, a);
+  load_luma_block<VEC>(wmk + org, g.row_pitch, col, a);
   const float sw = tmf::sigma0_block_faithful(a, nullptr);
-  load_luma_block<VEC>(orig + org, g.row_pitch, a);
+  load_luma_block<VEC>(orig + org, g.row_pitch, col, a);
   const float so = tmf::sigma0_block_faithful(a, nullptr);
   out_wm[gb] = (uint8_t)tmf::extract_level(sw, so, alpha);
 }
@@ -204,8 +244,10 @@ k_sigma0_faithful(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, B
   if (gb >= g.total_blocks) return;
   long long img; int by, bx;
   const size_t org = block_origin(g, gb, img, by, bx);
+  __shared__ float sm[64 * kThreads];
+  float* col = sm + threadIdx.x;
   float a[64];
-  load_luma_block<VEC>(rgb + org, g.row_pitch, a);
+  load_luma_block<VEC>(rgb + org, g.row_pitch, col, a);
   sigma0[gb] = tmf::sigma0_block_faithful(a, nullptr);
 }
 
@@ -216,24 +258,52 @@ k_sigma0_faithful(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, B
 // byte B of the 24-byte row as a float, via the 2^23 magic number (PRMT + FADD,
 // both full-rate pipes; the I2F.U8 conversion pipe is much narrower)
 __device__ __forceinline__ float byte_to_float(const uint32_t (&w)[6], int B) {
-  const uint32_t m = __byte_perm(w[B >> 2], 0x4B000000u, 0x7650u | (uint32_t)(B & 3));
+  const uint32_t x = w[B >> 2];
+  uint32_t m;
+  if ((B & 3) == 0) m = (x & 0xffu) | 0x4B000000u;                       // one LOP3
+  else if ((B & 3) == 3) m = __funnelshift_r(x, 0x004B0000u, 24);         // one SHF: (x >> 24) | 0x4B000000
+  else m = __byte_perm(x, 0x4B000000u, 0x7650u | (uint32_t)(B & 3));      // PRMT (half rate)
   return __uint_as_float(m) - 8388608.0f;
 }
 
+// one 24-byte block row -> r, g, b of its 8 pixels as floats in 0..255
 template <int VEC>
-__device__ __forceinline__ void load_luma255_block(const uint8_t* __restrict__ base, size_t pitch, float* a) {
+__device__ __forceinline__ void load_row_rgb255(const uint8_t* __restrict__ p, float (&r)[8], float (&g)[8], float (&b)[8]) {
+  uint32_t w[6];
+  load_row24<VEC>(p, w);
 #pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    r[j] = byte_to_float(w, 3 * j);
+    g[j] = byte_to_float(w, 3 * j + 1);
+    b[j] = byte_to_float(w, 3 * j + 2);
+  }
+}
+
+// pass 1 over the 8 rows of a block: Gram matrix of its luma (rolled loop: small code).
+// With KEEP, row i's luma is parked in shared memory as two float4 at
+// col[(2i) * kThreads] and col[(2i+1) * kThreads] (thread-private column,
+// conflict-free 128-bit accesses) for pass 2.
+template <int VEC, bool KEEP>
+__device__ __forceinline__ void gram_of_block(const uint8_t* __restrict__ base, size_t pitch, float (&gm)[36],
+                                              float4* __restrict__ col = nullptr) {
+#pragma unroll
+  for (int k = 0; k < 36; ++k) gm[k] = 0.0f;
+#pragma unroll kRowUnroll
   for (int i = 0; i < 8; ++i) {
-    uint32_t w[6];
-    load_row24<VEC>(base + (size_t)i * pitch, w);
+    float r[8], g[8], b[8], y[8];
+    load_row_rgb255<VEC>(base + (size_t)i * pitch, r, g, b);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      a[8 * i + j] = tmf::luma255_fast(byte_to_float(w, 3 * j), byte_to_float(w, 3 * j + 1), byte_to_float(w, 3 * j + 2));
+    for (int j = 0; j < 8; ++j) y[j] = tmf::luma255_fast(r[j], g[j], b[j]);
+    if (KEEP) {
+      col[(2 * i) * kThreads] = make_float4(y[0], y[1], y[2], y[3]);
+      col[(2 * i + 1) * kThreads] = make_float4(y[4], y[5], y[6], y[7]);
+    }
+    tmf::gram_accumulate_row(y, gm);
   }
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, TMF_FAST_MIN_CTAS)
 k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGeom g,
              const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
   const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -241,54 +311,59 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
   long long img; int by, bx;
   const size_t org = block_origin(g, gb, img, by, bx);
   const uint8_t* src = rgb + org;
-  float a[64];
-  load_luma255_block<VEC>(src, g.row_pitch, a);
+  __shared__ float4 lum[16 * kThreads];      // 32 KB: the block's luma, thread-private column
+  float4* col = lum + threadIdx.x;
+  float gm[36], w[8], f, c;
+  prefetch_block_rows(src, g.row_pitch);
+  gram_of_block<VEC, true>(src, g.row_pitch, gm, col);
   const long long wi = (wm_shared ? 0 : img * g.blocks_per_img) + (long long)by * g.nbw + bx;
-  tmf::embed_block_fast(a, alpha, (uint32_t)__ldg(wm + wi), nullptr);
+  tmf::embed_block_scalars_fast(gm, alpha, (uint32_t)__ldg(wm + wi), w, f, c, nullptr);
+  // pass 2: the rows again (L1/L2 hits), rank-1 update, colour out, quantise, store
   uint8_t* dst = out + org;
-#pragma unroll
+#pragma unroll kRowUnroll
   for (int i = 0; i < 8; ++i) {
-    uint32_t w[6], o[6] = {0, 0, 0, 0, 0, 0};
-    load_row24<VEC>(src + (size_t)i * g.row_pitch, w);
+    float r[8], gg[8], b[8];
+    int q[24];
+    uint32_t o[6];
+    load_row_rgb255<VEC>(src + (size_t)i * g.row_pitch, r, gg, b);
+    const float4 ya = col[(2 * i) * kThreads], yb = col[(2 * i + 1) * kThreads];
+    const float y[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+    tmf::embed_row_fast(r, gg, b, y, w, f, c, q);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float R, G, B;
-      tmf::rgb255_out_fast(byte_to_float(w, 3 * j), byte_to_float(w, 3 * j + 1), byte_to_float(w, 3 * j + 2),
-                           a[8 * i + j], R, G, B);
-      o[(3 * j) >> 2] |= tmf::quant255(R) << (8 * ((3 * j) & 3));
-      o[(3 * j + 1) >> 2] |= tmf::quant255(G) << (8 * ((3 * j + 1) & 3));
-      o[(3 * j + 2) >> 2] |= tmf::quant255(B) << (8 * ((3 * j + 2) & 3));
-    }
+    for (int k = 0; k < 6; ++k) o[k] = tmf::pack4_sat_u8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
     store_row24<VEC>(dst + (size_t)i * g.row_pitch, o);
   }
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, TMF_FAST_MIN_CTAS)
 k_extract_fast(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ orig, uint8_t* __restrict__ out_wm,
                BlockGeom g, double alpha) {
   const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (gb >= g.total_blocks) return;
   long long img; int by, bx;
   const size_t org = block_origin(g, gb, img, by, bx);
-  float a[64];
-  load_luma255_block<VEC>(wmk + org, g.row_pitch, a);
-  const float sw = tmf::sigma0_block_fast(a, nullptr);
-  load_luma255_block<VEC>(orig + org, g.row_pitch, a);
-  const float so = tmf::sigma0_block_fast(a, nullptr);
+  float gm[36];
+  prefetch_block_rows(wmk + org, g.row_pitch);
+  prefetch_block_rows(orig + org, g.row_pitch);
+  gram_of_block<VEC, false>(wmk + org, g.row_pitch, gm);
+  const float sw = tmf::sigma0_from_gram_fast(gm, nullptr);
+  gram_of_block<VEC, false>(orig + org, g.row_pitch, gm);
+  const float so = tmf::sigma0_from_gram_fast(gm, nullptr);
   out_wm[gb] = (uint8_t)tmf::extract_level(sw, so, alpha);
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, TMF_FAST_MIN_CTAS)
 k_sigma0_fast(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, BlockGeom g) {
   const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (gb >= g.total_blocks) return;
   long long img; int by, bx;
   const size_t org = block_origin(g, gb, img, by, bx);
-  float a[64];
-  load_luma255_block<VEC>(rgb + org, g.row_pitch, a);
-  sigma0[gb] = tmf::sigma0_block_fast(a, nullptr);
+  float gm[36];
+  prefetch_block_rows(rgb + org, g.row_pitch);
+  gram_of_block<VEC, false>(rgb + org, g.row_pitch, gm);
+  sigma0[gb] = tmf::sigma0_from_gram_fast(gm, nullptr);
 }
 
 // ---------------------------------------------------------------------------

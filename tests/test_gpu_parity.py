@@ -390,3 +390,29 @@ def test_host_pipeline_matches_device_path():
     if torch.cuda.device_count() > 1:
         two = W.embed_watermark_batch(imgs, wm, devices=[0, 1])
         assert np.array_equal(two, direct)
+
+
+# --------------------------------------------------------------------------- QR payload end to end (north_star)
+@pytest.mark.parametrize("mode", MODES)
+def test_qr_payload_bit_exact_through_the_drop_in_api(mode):
+    """text -> AES -> base64 -> QR (ECC H) -> PNG bytes -> embed_watermark(preserve_ratio=True)
+    -> extract_watermark -> QR decode -> AES decrypt, exactly the pages' flow
+    (embed_watermark_page.py:471-531, extract_watermark_page.py:293-369), GPU vs oracle."""
+    import qr_util as Q
+
+    text = "Test" * 10
+    png = Q.qr_png(Q.encrypt(text))
+    rgb = natural_like(1080, 1920, 21)
+    s = {"block_size": 8, "alpha": 0.1, "mode": mode}
+    img = Image.fromarray(rgb)
+    out = W.embed_watermark(img, png, preserve_ratio=True, custom_settings=s)
+    ext = W.extract_watermark(out, img, custom_settings=s)
+    got = Q.decode_map(np.array(ext))
+    assert got is not None and Q.decrypt(got) == text
+    wm = np.array(O.resize_watermark(png, 135, 240, True))
+    ref = O.embed_array(rgb, wm)
+    ref_ext = O.extract_array(ref, rgb)
+    assert Q.decode_map(ref_ext) == got                                   # same bytes as the reference path
+    assert_pixels(np.array(out), ref, what="1080p QR embed")
+    assert_extract(np.array(W.extract_watermark(Image.fromarray(ref), img, custom_settings=s)), ref_ext, "1080p QR extract")
+    assert Q.decode_map(O.extract_array(np.array(out), rgb)) == got       # reference extractor on the GPU's image

@@ -98,3 +98,39 @@ def test_dct_and_colour_math():
     assert np.abs(H.dct(O.dct_blocks(b), inverse=True) - b).max() <= 2e-6
     rgb = rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)
     assert np.array_equal(H.rgb2ycc(rgb), O.rgb_to_ycbcr(rgb))
+
+
+_QR_CASE = {}
+
+
+def _qr_case():
+    """1080p natural-like image + a 40-character text as an AES'd QR watermark, through the
+    oracle once (about 6 s)."""
+    if not _QR_CASE:
+        import qr_util as Q
+
+        text = "Test" * 10
+        png = Q.qr_png(Q.encrypt(text))
+        rgb = natural_like(1080, 1920, 21)
+        wm = np.array(O.resize_watermark(png, 135, 240, True))
+        ref = O.embed_array(rgb, wm)
+        _QR_CASE.update(text=text, png=png, rgb=rgb, wm=wm, ref=ref, ref_ext=O.extract_array(ref, rgb))
+    return _QR_CASE
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_qr_payload_survives_embed_extract(mode):
+    """north_star: QR payload bit-exact.  text -> AES -> base64 -> QR -> PNG ->
+    resize_watermark(preserve_ratio) -> embed -> extract -> QR decode -> AES."""
+    import qr_util as Q
+
+    c = _qr_case()
+    ref_payload = Q.decode_map(c["ref_ext"])
+    assert ref_payload is not None and Q.decrypt(ref_payload) == c["text"]      # the reference path itself works
+    out, _, _ = H.embed(c["rgb"], c["wm"], mode=mode)
+    assert np.abs(out.astype(int) - c["ref"].astype(int)).max() <= 1
+    got = Q.decode_map(H.extract(out, c["rgb"], mode=mode))
+    assert got == ref_payload and Q.decrypt(got) == c["text"]
+    # cross paths decode to the same bytes
+    assert Q.decode_map(O.extract_array(out, c["rgb"])) == ref_payload
+    assert Q.decode_map(H.extract(c["ref"], c["rgb"], mode=mode)) == ref_payload

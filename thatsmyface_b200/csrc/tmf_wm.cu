@@ -40,6 +40,9 @@ constexpr int kThreads = 128;
 #ifndef TMF_ROW_UNROLL
 #define TMF_ROW_UNROLL 1      // rows per iteration of the rolled row loops (1, 2, 4)
 #endif
+#ifndef TMF_L2_LOOKAHEAD
+#define TMF_L2_LOOKAHEAD 0    // blocks ahead whose rows are prefetched into L2 (0 = off)
+#endif
 #ifndef TMF_FAST_MIN_CTAS
 #define TMF_FAST_MIN_CTAS 6   // __launch_bounds__ minimum CTAs/SM of the fast kernels
 #endif
@@ -257,13 +260,16 @@ k_sigma0_faithful(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, B
 // ---------------------------------------------------------------------------
 // byte B of the 24-byte row as a float, via the 2^23 magic number (PRMT + FADD,
 // both full-rate pipes; the I2F.U8 conversion pipe is much narrower)
-__device__ __forceinline__ float byte_to_float(const uint32_t (&w)[6], int B) {
+// byte B of the row as the "magic" float 2^23 + k (one half-rate PRMT or SHF; the
+// bit pattern 0x4B0000kk is exactly 8388608 + k)
+__device__ __forceinline__ float byte_to_magic(const uint32_t (&w)[6], int B) {
   const uint32_t x = w[B >> 2];
-  uint32_t m;
-  if ((B & 3) == 0) m = (x & 0xffu) | 0x4B000000u;                       // one LOP3
-  else if ((B & 3) == 3) m = __funnelshift_r(x, 0x004B0000u, 24);         // one SHF: (x >> 24) | 0x4B000000
-  else m = __byte_perm(x, 0x4B000000u, 0x7650u | (uint32_t)(B & 3));      // PRMT (half rate)
-  return __uint_as_float(m) - 8388608.0f;
+  const uint32_t m = ((B & 3) == 3) ? __funnelshift_r(x, 0x004B0000u, 24)        // (x >> 24) | 0x4B000000
+                                    : __byte_perm(x, 0x4B000000u, 0x7650u | (uint32_t)(B & 3));
+  return __uint_as_float(m);
+}
+__device__ __forceinline__ float byte_to_float(const uint32_t (&w)[6], int B) {
+  return byte_to_magic(w, B) - 8388608.0f;
 }
 
 // one 24-byte block row -> r, g, b of its 8 pixels as floats in 0..255
@@ -279,6 +285,13 @@ __device__ __forceinline__ void load_row_rgb255(const uint8_t* __restrict__ p, f
   }
 }
 
+// Prefetch into L2 the rows of the block a later wave of CTAs will own, turning
+// its DRAM latency into L2 latency.
+__device__ __forceinline__ void prefetch_block_rows_l2(const uint8_t* __restrict__ base, size_t pitch) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)i * pitch));
+}
+
 // pass 1 over the 8 rows of a block: Gram matrix of its luma (rolled loop: small code).
 // With KEEP, row i's luma is parked in shared memory as two float4 at
 // col[(2i) * kThreads] and col[(2i+1) * kThreads] (thread-private column,
@@ -290,10 +303,16 @@ __device__ __forceinline__ void gram_of_block(const uint8_t* __restrict__ base, 
   for (int k = 0; k < 36; ++k) gm[k] = 0.0f;
 #pragma unroll kRowUnroll
   for (int i = 0; i < 8; ++i) {
-    float r[8], g[8], b[8], y[8];
-    load_row_rgb255<VEC>(base + (size_t)i * pitch, r, g, b);
+    float y[8];
+    uint32_t w[6];
+    load_row24<VEC>(base + (size_t)i * pitch, w);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) y[j] = tmf::luma255_fast(r[j], g[j], b[j]);
+    for (int j = 0; j < 8; ++j) {
+      // fma(c, 2^23 + b, -c 2^23) == RN(c b) exactly (one rounding of an exact sum), so the
+      // blue byte needs no separate magic subtraction; same value as luma255_fast
+      const float tb = fmaf(0.114f, byte_to_magic(w, 3 * j + 2), -0.114f * 8388608.0f);
+      y[j] = fmaf(0.299f, byte_to_float(w, 3 * j), fmaf(0.587f, byte_to_float(w, 3 * j + 1), tb));
+    }
     if (KEEP) {
       col[(2 * i) * kThreads] = make_float4(y[0], y[1], y[2], y[3]);
       col[(2 * i + 1) * kThreads] = make_float4(y[4], y[5], y[6], y[7]);
@@ -315,6 +334,10 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
   float4* col = lum + threadIdx.x;
   float gm[36], w[8], f, c;
   prefetch_block_rows(src, g.row_pitch);
+  if (TMF_L2_LOOKAHEAD > 0 && gb + TMF_L2_LOOKAHEAD < g.total_blocks) {
+    long long img2; int by2, bx2;
+    prefetch_block_rows_l2(rgb + block_origin(g, gb + TMF_L2_LOOKAHEAD, img2, by2, bx2), g.row_pitch);
+  }
   gram_of_block<VEC, true>(src, g.row_pitch, gm, col);
   const long long wi = (wm_shared ? 0 : img * g.blocks_per_img) + (long long)by * g.nbw + bx;
   tmf::embed_block_scalars_fast(gm, alpha, (uint32_t)__ldg(wm + wi), w, f, c, nullptr);
@@ -346,6 +369,12 @@ k_extract_fast(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ orig
   float gm[36];
   prefetch_block_rows(wmk + org, g.row_pitch);
   prefetch_block_rows(orig + org, g.row_pitch);
+  if (TMF_L2_LOOKAHEAD > 0 && gb + TMF_L2_LOOKAHEAD < g.total_blocks) {
+    long long img2; int by2, bx2;
+    const size_t o2 = block_origin(g, gb + TMF_L2_LOOKAHEAD, img2, by2, bx2);
+    prefetch_block_rows_l2(wmk + o2, g.row_pitch);
+    prefetch_block_rows_l2(orig + o2, g.row_pitch);
+  }
   gram_of_block<VEC, false>(wmk + org, g.row_pitch, gm);
   const float sw = tmf::sigma0_from_gram_fast(gm, nullptr);
   gram_of_block<VEC, false>(orig + org, g.row_pitch, gm);

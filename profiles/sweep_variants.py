@@ -14,8 +14,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
-VARIANTS = {f"u{u}_c{c}_l{l // 1000}k": {"TMF_ROW_UNROLL": u, "TMF_FAST_MIN_CTAS": c, "TMF_L2_LOOKAHEAD": l}
-            for u, c, l in itertools.product((1, 2), (4, 6), (0, 113664, 227328))}
+VARIANTS = {f"u{u}_c{c}_t{t}": {"TMF_ROW_UNROLL": u, "TMF_FAST_MIN_CTAS": c, "TMF_EMBED_THREADS": t}
+            for u, c, t in itertools.product((1, 2), (4, 6), (128, 256, 384))}
 
 
 def build():

@@ -37,9 +37,6 @@
 
 namespace tmf {
 
-#define TMF_FAST_TOL_EMBED 2.0e-3f     // slow path: 1 - tr(P) at which P's top column is v0 to ~1e-6
-#define TMF_FAST_TOL_EXTRACT 3.0e-2f   // extract needs sigma0 only (second order in the vector error)
-#define TMF_FAST_MAX_SQUARINGS 18
 
 // upper triangle of a symmetric 8x8 in 36 registers: index of (i, j), i <= j
 #define TMF_SYM(i, j) ((i) * 8 - ((i) * ((i) + 1)) / 2 + (j))
@@ -92,89 +89,81 @@ TMF_HD float dot8(const float* a, const float* b) {
   return s;
 }
 
-// Slow path: repeated squaring of a copy of the unit-trace M; rigorous for any
-// spectral gap.  w = unit top eigenvector, mu = w.Mw.  Returns the squarings.
-TMF_HD int top_pair_by_squaring(const float* m, float tol, float* w, float& ww, float& mu) {
-  float q[36], p[36];
-#pragma unroll
-  for (int k = 0; k < 36; ++k) q[k] = m[k];
-  int it = 0;
-  for (;;) {
-    const float t = sym_square(q, p);     // tr(q) == 1, so t = sum of squared eigenvalue shares
-    ++it;
-    if (1.0f - t <= tol || it >= TMF_FAST_MAX_SQUARINGS) break;
-    const float inv = f_rcp_fast(t);
-#pragma unroll
-    for (int k = 0; k < 36; ++k) q[k] = p[k] * inv;
-  }
-  // column of p with the largest diagonal entry (>= 1/8 of the trace)
-  float best = p[TMF_SYM(0, 0)];
-  int col = 0;
-#pragma unroll
-  for (int j = 1; j < 8; ++j) {
-    const float d = p[TMF_SYM(j, j)];
-    if (d > best) { best = d; col = j; }
-  }
-  float y[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float x = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x = (j == col) ? TMF_SYMG(p, i, j) : x;
-    y[i] = x;
-  }
-  const float n2 = dot8(y, y);
-  float rn = f_rsqrt(n2);
-  rn = fmaf(0.5f * rn, fmaf(-n2 * rn, rn, 1.0f), rn);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) w[i] = y[i] * rn;
-  float mw[8];
-  sym_matvec(m, w, mw);
-  ww = dot8(w, w);
-  mu = dot8(w, mw) * f_rcp_fast(ww);
-  return it;
-}
+// Top eigenpair of the unit-trace Gram matrix m (entrywise >= 0; DESTROYED) of a
+// luma block: certified power iteration with adaptive squaring.
+//
+//   level 0: v = 1 (tan(angle to v0) <= sqrt7 by Perron-Frobenius), x = M v, y = M x.
+//   The Rayleigh quotient of x gives rho^ = (1 - mu^)/mu^ >= mu_1/mu_0 (unit trace), so
+//   tan(angle(y)) <= theta * rho^^2, and every further product multiplies the bound by
+//   rho^.  If at most 3 more products reach the tolerance, do them and stop.
+//   Otherwise square: M <- M^2 / tr(M^2) (eigenvalue ratios are squared, trace is 1
+//   again), keep y as the start vector with its bound, and repeat.  Textured blocks take
+//   one squaring, near-tied ones a few; the bound is rigorous for any gap.
+//
+// On return w (not normalised, ww = w.w) spans v0 to `tol` and mu ~ mu_0 of the ORIGINAL
+// m to ~1e-7 (mu_l = sqrt(mu_{l+1} tr(M_l^2)) unwinds the squarings).  Returns
+// products + 100 * squarings.
+#define TMF_FAST_TOL_VEC_EMBED 1.0e-6f     // u0 v0^T itself is used
+#define TMF_FAST_TOL_VEC_EXTRACT 3.0e-4f   // sigma0 only: second order in the vector error
+#define TMF_FAST_MAX_LEVELS 18
 
-// Top eigenpair of the unit-trace Gram matrix m (entrywise >= 0) of a luma block.
-// On return w (NOT normalised, ww = w.w) spans v0 and mu ~ mu_0 (relative 1e-7).
-// Returns the number of M products (fast path) or 100 + squarings (slow path).
 template <bool EMBED>
-TMF_HD int top_pair(const float* m, float* w, float& ww, float& mu) {
-  float x[8], y[8];
+TMF_HD int top_pair(float* m, float* w, float& ww, float& mu) {
+  const float tol = EMBED ? TMF_FAST_TOL_VEC_EMBED : TMF_FAST_TOL_VEC_EXTRACT;
+  float x[8], y[8], tr2[TMF_FAST_MAX_LEVELS];
+  float theta = 2.6457513f;              // sqrt(7)
+  int level = 0, products = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {          // x = M 1
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s += TMF_SYMG(m, i, j);
-    x[i] = s;
-  }
-  sym_matvec(m, x, y);                   // y = M^2 1
-  float xx = dot8(x, x), xy = dot8(x, y), yy = dot8(y, y);
-  const float rho = fmaxf(xx - xy, 0.0f) * f_rcp_fast(xy);
-  // embed: sqrt7 rho^J <= 1e-6 (u0 v0^T itself);  extract: 7 rho^(2J-1) <= 1e-7 (sigma0 only)
-  const float r2 = EMBED ? 6.1e-4f : 2.4e-3f;
-  const float r3 = EMBED ? 7.2e-3f : 2.7e-2f;
-  const float r4 = EMBED ? 2.48e-2f : 7.5e-2f;
-  const float r5 = EMBED ? 5.2e-2f : 1.34e-1f;
-  if (rho <= r5) {
-    const int more = (rho <= r2) ? 0 : (rho <= r3) ? 1 : (rho <= r4) ? 2 : 3;
+  for (int i = 0; i < 8; ++i) y[i] = 1.0f;
+  float xy, yy;
+  for (;;) {
+    sym_matvec(m, y, x);                 // x = M v      (v is y from the previous level, or ones)
+    sym_matvec(m, x, y);                 // y = M x
+    products += 2;
+    const float xx = dot8(x, x);
+    xy = dot8(x, y);
+    yy = dot8(y, y);
+    const float rho = fmaxf(xx - xy, 0.0f) * f_rcp_fast(xy);
+    float err = theta * rho * rho;       // bound on tan(angle(y, v0))
+    int more = 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      if (k < more) {
-        sym_matvec(m, y, x);             // x = M y
-        xy = dot8(y, x);                 // w_{J-1}.w_J
-        yy = dot8(x, x);                 // w_J.w_J
-#pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = x[i];
-      }
+      if (err > tol) { err *= rho; ++more; }
     }
+    if (err <= tol || level >= TMF_FAST_MAX_LEVELS - 1) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = y[i];
-    ww = yy;
-    mu = yy * f_rcp_fast(xy);
-    return 2 + more;
+      for (int k = 0; k < 3; ++k) {
+        if (k < more) {
+          sym_matvec(m, y, x);           // x = M y
+          xy = dot8(y, x);               // w_{J-1}.w_J
+          yy = dot8(x, x);               // w_J.w_J
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = x[i];
+        }
+      }
+      products += more;
+      break;
+    }
+    // square in place: M <- M^2 / tr(M^2)
+    float p[36];
+    const float t = sym_square(m, p);
+    tr2[level] = t;
+    const float inv = f_rcp_fast(t);
+#pragma unroll
+    for (int k = 0; k < 36; ++k) m[k] = p[k] * inv;
+    // carry y over as the next start vector, rescaled so nothing underflows
+    const float rn = f_rsqrt(yy);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] *= rn;
+    theta = fminf(theta * rho * rho, 2.6457513f);
+    ++level;
   }
-  return 100 + top_pair_by_squaring(m, EMBED ? TMF_FAST_TOL_EMBED : TMF_FAST_TOL_EXTRACT, w, ww, mu);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = y[i];
+  ww = yy;
+  mu = yy * f_rcp_fast(xy);              // (w_J.w_J)/(w_{J-1}.w_J) <= mu_0 of the current level
+  for (int l = level - 1; l >= 0; --l) mu = f_sqrt(mu * tr2[l]);
+  return products + 100 * level;
 }
 
 // Per-block scalars of the embed, from the Gram matrix accumulated in pass 1

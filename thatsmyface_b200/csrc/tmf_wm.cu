@@ -296,7 +296,7 @@ __device__ __forceinline__ void prefetch_block_rows_l2(const uint8_t* __restrict
 // With KEEP, row i's luma is parked in shared memory as two float4 at
 // col[(2i) * kThreads] and col[(2i+1) * kThreads] (thread-private column,
 // conflict-free 128-bit accesses) for pass 2.
-template <int VEC, bool KEEP>
+template <int VEC, bool KEEP, int STRIDE = kThreads>
 __device__ __forceinline__ void gram_of_block(const uint8_t* __restrict__ base, size_t pitch, float (&gm)[36],
                                               float4* __restrict__ col = nullptr) {
 #pragma unroll
@@ -314,13 +314,22 @@ __device__ __forceinline__ void gram_of_block(const uint8_t* __restrict__ base, 
       y[j] = fmaf(0.299f, byte_to_float(w, 3 * j), fmaf(0.587f, byte_to_float(w, 3 * j + 1), tb));
     }
     if (KEEP) {
-      col[(2 * i) * kThreads] = make_float4(y[0], y[1], y[2], y[3]);
-      col[(2 * i + 1) * kThreads] = make_float4(y[4], y[5], y[6], y[7]);
+      col[(2 * i) * STRIDE] = make_float4(y[0], y[1], y[2], y[3]);
+      col[(2 * i + 1) * STRIDE] = make_float4(y[4], y[5], y[6], y[7]);
     }
     tmf::gram_accumulate_row(y, gm);
   }
 }
 
+// Fused embed, FAST mode.
+//
+// Blocks whose watermark value is 0 get d = f32(f64(s0) + alpha*0) - s0 = 0 exactly
+// (watermarking.py:198): their output is the colour round trip alone, so a lane with a
+// zero mark skips pass 1 and the eigenpair (a whole warp of zero marks - black areas of
+// the map - saves the issue slots; in a mixed warp the lane just idles).  Sorting the
+// blocks of a CTA so that warps become uniform was measured and is slower: the scattered
+// 24-byte row pieces cost more L1 wavefronts than the skipped work saves
+// (profiles/r01_sweep_variants.txt, third table).
 template <int VEC>
 __global__ void __launch_bounds__(kThreads, TMF_FAST_MIN_CTAS)
 k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGeom g,
@@ -332,15 +341,18 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
   const uint8_t* src = rgb + org;
   __shared__ float4 lum[16 * kThreads];      // 32 KB: the block's luma, thread-private column
   float4* col = lum + threadIdx.x;
-  float gm[36], w[8], f, c;
   prefetch_block_rows(src, g.row_pitch);
-  if (TMF_L2_LOOKAHEAD > 0 && gb + TMF_L2_LOOKAHEAD < g.total_blocks) {
-    long long img2; int by2, bx2;
-    prefetch_block_rows_l2(rgb + block_origin(g, gb + TMF_L2_LOOKAHEAD, img2, by2, bx2), g.row_pitch);
-  }
-  gram_of_block<VEC, true>(src, g.row_pitch, gm, col);
   const long long wi = (wm_shared ? 0 : img * g.blocks_per_img) + (long long)by * g.nbw + bx;
-  tmf::embed_block_scalars_fast(gm, alpha, (uint32_t)__ldg(wm + wi), w, f, c, nullptr);
+  const uint32_t mark = (uint32_t)__ldg(wm + wi);
+  float w[8], f = 0.0f, c = 0.0f;
+  if (mark != 0) {
+    float gm[36];
+    gram_of_block<VEC, true>(src, g.row_pitch, gm, col);
+    tmf::embed_block_scalars_fast(gm, alpha, mark, w, f, c, nullptr);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = 0.0f;
+  }
   // pass 2: the rows again (L1/L2 hits), rank-1 update, colour out, quantise, store
   uint8_t* dst = out + org;
 #pragma unroll kRowUnroll
@@ -349,7 +361,8 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
     int q[24];
     uint32_t o[6];
     load_row_rgb255<VEC>(src + (size_t)i * g.row_pitch, r, gg, b);
-    const float4 ya = col[(2 * i) * kThreads], yb = col[(2 * i + 1) * kThreads];
+    float4 ya = make_float4(0.f, 0.f, 0.f, 0.f), yb = ya;
+    if (mark != 0) { ya = col[(2 * i) * kThreads]; yb = col[(2 * i + 1) * kThreads]; }
     const float y[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
     tmf::embed_row_fast(r, gg, b, y, w, f, c, q);
 #pragma unroll

@@ -130,8 +130,11 @@ def embed_tensor(rgb, wm, alpha=ALPHA, block_size=BLOCK_SIZE, mode=None, out=Non
         raise ValueError(f"watermark map must be {(nbh, nbw)} or {(n, nbh, nbw)}, got {tuple(wm.shape)}")
     if out is None:
         out = torch.empty_like(x)
-    elif out.shape != x.shape or out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous():
-        raise ValueError("out must be a contiguous CUDA uint8 tensor shaped like rgb")
+    else:
+        if out.dim() == 3:
+            out = out.unsqueeze(0)
+        if out.shape != x.shape or out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous():
+            raise ValueError("out must be a contiguous CUDA uint8 tensor shaped like rgb")
     lib = _lib.load()
     with torch.cuda.device(x.device):
         _lib.check(lib.tmf_embed_rgb8(x.data_ptr(), out.data_ptr(), n, h, w, h * w * 3, wm.data_ptr(), shared,
@@ -153,6 +156,12 @@ def extract_tensor(wmk, orig, alpha=ALPHA, block_size=BLOCK_SIZE, mode=None, out
     n, h, w, _ = a.shape
     if out is None:
         out = torch.empty((n, h // 8, w // 8), dtype=torch.uint8, device=a.device)
+    else:
+        if out.dim() == 2:
+            out = out.unsqueeze(0)
+        if (tuple(out.shape) != (n, h // 8, w // 8) or out.dtype != torch.uint8 or not out.is_cuda
+                or not out.is_contiguous()):
+            raise ValueError(f"out must be a contiguous CUDA uint8 tensor of shape {(n, h // 8, w // 8)}")
     lib = _lib.load()
     with torch.cuda.device(a.device):
         _lib.check(lib.tmf_extract_rgb8(a.data_ptr(), b.data_ptr(), out.data_ptr(), n, h, w, h * w * 3,

@@ -38,6 +38,26 @@ ALPHA, BLOCK = 0.1, 8
 METRIC = "megapixels/sec DCT+SVD embed (1080p batch, fused kernel); extract and roofline alongside"
 
 
+# --------------------------------------------------------------------------- stdout hygiene
+_REAL_STDOUT_FD = None
+
+
+def _own_stdout():
+    """Exactly ONE line may reach stdout (the JSON).  Libraries print there too (NCCL's
+    version banner comes from C code), so park the real stdout and point fd 1 at stderr."""
+    global _REAL_STDOUT_FD
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.flush()
+        _REAL_STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT_FD if _REAL_STDOUT_FD is not None else 1, data)
+
+
 # --------------------------------------------------------------------------- synthetic data
 def make_wm_map():
     """Shared 135x240 map: a QR-like 41x41-module random pattern, 3 px per module,
@@ -221,7 +241,7 @@ def reference_arm(args):
         "e2e": {"value": round(value, 4), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -237,6 +257,7 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "faithful"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _own_stdout()
     if args.impl == "reference":
         return reference_arm(args)
     if args.warmup < 3:
@@ -402,7 +423,7 @@ def main():
         "other_mode": {"mode": "faithful" if other == MODE_FAITHFUL else "fast", "value_1gpu": round(other_value, 1),
                        "unit": "MP/s", "images": m},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

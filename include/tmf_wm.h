@@ -41,7 +41,8 @@ extern "C" {
 enum {
   TMF_OK = 0,
   TMF_ERR_BAD_ARG = -1,           /* null pointer, negative size, bad stride, bad mode */
-  TMF_ERR_UNSUPPORTED_BLOCK = -2, /* block_size other than 8 (the reference's BLOCK_SIZE, constants.py:7) */
+  TMF_ERR_UNSUPPORTED_BLOCK = -2, /* block_size not one of 4, 6, 8, 10, 12, 14, 16 (the UI's range,
+                                     embed_watermark_page.py:324-331); 8 = BLOCK_SIZE, constants.py:7 */
   TMF_ERR_CUDA = -3               /* CUDA runtime / launch failure (message has the CUDA error string) */
 };
 
@@ -59,21 +60,25 @@ const char* tmf_last_error(void);
 /* Number of CUDA devices visible, or a negative error. */
 int tmf_device_count(void);
 
-/* embed_watermark on a batch.  rgb/out: n images of h x w x 3 bytes (out may not
- * alias rgb).  wm: watermark map(s), (h/8) x (w/8) bytes each, already resized
+/* `block` is the reference's block_size: 8 runs the tuned kernels (both modes); the
+ * other even sizes 4..16 run a generic kernel that uses the FAST algebra whatever `mode`
+ * says.  Below, B = block.
+ *
+ * embed_watermark on a batch.  rgb/out: n images of h x w x 3 bytes (out may not
+ * alias rgb).  wm: watermark map(s), (h/B) x (w/B) bytes each, already resized
  * (resize_watermark stays on the host, watermarking.py:86-132); one map per
  * image, or a single shared map when wm_shared != 0.  Pixels outside whole
- * blocks (h%8, w%8 strips) take the colour round trip only, as in the
+ * blocks (h%B, w%B strips) take the colour round trip only, as in the
  * reference.  alpha is double because the reference adds alpha*w in float64
  * (watermarking.py:198). */
 int tmf_embed_rgb8(const uint8_t* rgb, uint8_t* out, int n, int h, int w, size_t img_stride,
                    const uint8_t* wm, int wm_shared, double alpha, int block, int mode, void* stream);
 
-/* extract_watermark on a batch.  out_wm: n maps of (h/8) x (w/8) bytes. */
+/* extract_watermark on a batch.  out_wm: n maps of (h/B) x (w/B) bytes. */
 int tmf_extract_rgb8(const uint8_t* wmk_rgb, const uint8_t* orig_rgb, uint8_t* out_wm, int n, int h, int w,
                      size_t img_stride, double alpha, int block, int mode, void* stream);
 
-/* Tap: largest singular value of every whole luma block, float32, n x (h/8) x (w/8). */
+/* Tap: largest singular value of every whole luma block, float32, n x (h/B) x (w/B). */
 int tmf_sigma0_rgb8(const uint8_t* rgb, float* sigma0, int n, int h, int w, size_t img_stride, int block,
                     int mode, void* stream);
 

@@ -124,6 +124,23 @@ def main():
         if not (ok_out and ok_ext and ok_loop and ok_y and ok_d):
             print("ORACLE MISMATCH in", name, file=sys.stderr)
 
+    # other block sizes / alphas of the UI sliders (embed_watermark_page.py:324-350)
+    for bs, alpha in ((4, 0.1), (6, 0.3), (12, 0.5), (16, 1.0)):
+        r2 = np.random.default_rng(100 + bs)
+        rgb = natural_like(5 * bs + 2, 6 * bs + 1, 30 + bs)
+        wm = np.where(r2.random((5, 6)) < 0.4, 0, r2.integers(1, 256, (5, 6))).astype(np.uint8)
+        st = {"block_size": bs, "alpha": alpha}
+        ref_out = np.array(R.embed_watermark(Image.fromarray(rgb), Image.fromarray(wm), False, dict(st)))
+        ref_ext = np.array(R.extract_watermark(Image.fromarray(ref_out), Image.fromarray(rgb), dict(st)))
+        ok_out = bool((O.embed_array(rgb, wm, alpha, bs) == ref_out).all())
+        ok_ext = bool((O.extract_array(ref_out, rgb, alpha, bs) == ref_ext).all())
+        name = f"bs{bs}_alpha{alpha}"
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), rgb=rgb, wm=wm, ref_out=ref_out, ref_ext=ref_ext,
+                            bs=np.int32(bs), alpha=np.float64(alpha))
+        report["cases"][name] = dict(shape=list(rgb.shape), sha_out=sha(ref_out), sha_ext=sha(ref_ext),
+                                     oracle_out_identical=ok_out, oracle_ext_identical=ok_ext)
+        print(name, report["cases"][name])
+
     # PIL-level path with a PNG-bytes watermark and LANCZOS + white padding
     rng = np.random.default_rng(5)
     qr_like = np.kron((rng.integers(0, 2, (25, 25)) * 255).astype(np.uint8), np.ones((8, 8), np.uint8))

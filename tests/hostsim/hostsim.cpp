@@ -128,6 +128,86 @@ int hostsim_extract_fast(const uint8_t* wmk, const uint8_t* orig, uint8_t* out, 
   return 0;
 }
 
+}  // extern "C"
+
+// ---- other block sizes (generic-N templates of tmf_fast.cuh)
+template <int N>
+static void gram_of_block_n(const uint8_t* rgb, int w, int by, int bx, float* gm) {
+  for (int k = 0; k < N * (N + 1) / 2; ++k) gm[k] = 0.0f;
+  for (int i = 0; i < N; ++i) {
+    float y[N];
+    for (int j = 0; j < N; ++j) {
+      const uint8_t* p = rgb + ((size_t)(by * N + i) * w + bx * N + j) * 3;
+      y[j] = luma255_fast((float)p[0], (float)p[1], (float)p[2]);
+    }
+    gram_accumulate_row<N>(y, gm);
+  }
+}
+
+template <int N>
+static void embed_n(const uint8_t* rgb, uint8_t* out, int h, int w, const uint8_t* wm, double alpha) {
+  const int nbh = h / N, nbw = w / N;
+  for (int by = 0; by < nbh; ++by)
+    for (int bx = 0; bx < nbw; ++bx) {
+      float gm[N * (N + 1) / 2], wv[N], f = 0.f, c = 0.f;
+      for (int i = 0; i < N; ++i) wv[i] = 0.f;
+      const uint32_t mark = wm[by * nbw + bx];
+      if (mark) {
+        gram_of_block_n<N>(rgb, w, by, bx, gm);
+        embed_block_scalars_fast<N>(gm, alpha, mark, wv, f, c, nullptr);
+      }
+      for (int i = 0; i < N; ++i) {
+        float r[N], g[N], b[N], y[N];
+        int q[3 * N];
+        for (int j = 0; j < N; ++j) {
+          const uint8_t* p = rgb + ((size_t)(by * N + i) * w + bx * N + j) * 3;
+          r[j] = (float)p[0]; g[j] = (float)p[1]; b[j] = (float)p[2];
+          y[j] = luma255_fast(r[j], g[j], b[j]);
+        }
+        embed_row_fast<N>(r, g, b, y, wv, f, c, q);
+        uint8_t* d = out + ((size_t)(by * N + i) * w + bx * N) * 3;
+        for (int k = 0; k < 3 * N; ++k) d[k] = (uint8_t)(q[k] < 0 ? 0 : (q[k] > 255 ? 255 : q[k]));
+      }
+    }
+}
+
+template <int N>
+static void extract_n(const uint8_t* wmk, const uint8_t* orig, uint8_t* out, int h, int w, double alpha) {
+  const int nbh = h / N, nbw = w / N;
+  for (int by = 0; by < nbh; ++by)
+    for (int bx = 0; bx < nbw; ++bx) {
+      float gm[N * (N + 1) / 2];
+      gram_of_block_n<N>(wmk, w, by, bx, gm);
+      float sw = sigma0_from_gram_fast<N>(gm, nullptr);
+      gram_of_block_n<N>(orig, w, by, bx, gm);
+      float so = sigma0_from_gram_fast<N>(gm, nullptr);
+      out[by * nbw + bx] = (uint8_t)extract_level(sw, so, alpha);
+    }
+}
+
+extern "C" {
+
+#define HOSTSIM_FOR_N(n, CALL) switch (n) { case 4: { CALL(4); } break; case 6: { CALL(6); } break; case 8: { CALL(8); } break; \
+  case 10: { CALL(10); } break; case 12: { CALL(12); } break; case 14: { CALL(14); } break; case 16: { CALL(16); } break; default: return -2; }
+
+int hostsim_embed_n(const uint8_t* rgb, uint8_t* out, int h, int w, const uint8_t* wm, double alpha, int bs) {
+  for (size_t p = 0; p < (size_t)h * w; ++p) {   // strips: exact colour round trip, as in the library
+    float r = unit_from_u8(rgb[3 * p]), g = unit_from_u8(rgb[3 * p + 1]), b = unit_from_u8(rgb[3 * p + 2]);
+    float cb, cr; chroma_exact(r, g, b, cb, cr);
+    uint32_t R, G, B; ycc_to_rgb8_exact(luma_exact(r, g, b), cb, cr, R, G, B);
+    out[3 * p] = (uint8_t)R; out[3 * p + 1] = (uint8_t)G; out[3 * p + 2] = (uint8_t)B;
+  }
+#define CALL_E(NN) embed_n<NN>(rgb, out, h, w, wm, alpha)
+  HOSTSIM_FOR_N(bs, CALL_E)
+  return 0;
+}
+
+int hostsim_extract_n(const uint8_t* wmk, const uint8_t* orig, uint8_t* out, int h, int w, double alpha, int bs) {
+#define CALL_X(NN) extract_n<NN>(wmk, orig, out, h, w, alpha)
+  HOSTSIM_FOR_N(bs, CALL_X)
+  return 0;
+}
+
 // full SVD of N row-major 8x8 blocks: S unsorted column norms, AV and V returned raw
 int hostsim_svd(const float* blocks, int64_t n, float* AV, float* V, float* S, int* sweeps) {
   for (int64_t b = 0; b < n; ++b) {

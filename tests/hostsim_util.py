@@ -72,3 +72,19 @@ def rgb2ycc(rgb):
     out = np.empty(rgb.shape, np.float32)
     lib().hostsim_rgb2ycc(_p(rgb), _p(out), C.c_int64(rgb.shape[0] * rgb.shape[1]))
     return out
+
+
+def embed_n(rgb, wm, alpha, bs):
+    rgb, wm = np.ascontiguousarray(rgb), np.ascontiguousarray(wm)
+    h, w = rgb.shape[:2]
+    out = np.empty_like(rgb)
+    assert lib().hostsim_embed_n(_p(rgb), _p(out), h, w, _p(wm), C.c_double(alpha), bs) == 0
+    return out
+
+
+def extract_n(a, b, alpha, bs):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    h, w = a.shape[:2]
+    out = np.zeros((h // bs, w // bs), np.uint8)
+    assert lib().hostsim_extract_n(_p(a), _p(b), _p(out), h, w, C.c_double(alpha), bs) == 0
+    return out

@@ -27,7 +27,8 @@ from thatsmyface_b200 import watermarking as W  # noqa: E402
 from thatsmyface_b200.constants import MODE_FAITHFUL, MODE_FAST  # noqa: E402
 
 MODES = [MODE_FAITHFUL, MODE_FAST]
-ARRAY_CASES = [n for n in golden_names() if not n.startswith("pil_")]
+ARRAY_CASES = [n for n in golden_names() if not n.startswith(("pil_", "bs"))]
+BS_CASES = [n for n in golden_names() if n.startswith("bs")]
 SIGMA_RTOL = 1e-5
 
 
@@ -329,10 +330,12 @@ def test_empty_and_sub_block_inputs():
 def test_errors_are_loud_and_typed():
     x = torch.zeros((16, 16, 3), dtype=torch.uint8, device="cuda")
     m = torch.zeros((2, 2), dtype=torch.uint8, device="cuda")
-    with pytest.raises(ValueError, match="block_size 4 is not supported"):
-        W.embed_tensor(x, m, block_size=4)
+    with pytest.raises(ValueError, match="block_size 5 is not supported"):
+        W.embed_tensor(x, m, block_size=5)
     with pytest.raises(ValueError, match="block_size"):
-        W.embed_watermark(Image.new("RGB", (16, 16)), Image.new("L", (2, 2)), False, {"block_size": 16, "alpha": 0.1})
+        W.embed_watermark(Image.new("RGB", (16, 16)), Image.new("L", (2, 2)), False, {"block_size": 18, "alpha": 0.1})
+    from thatsmyface_b200 import _lib
+    assert _lib.load().tmf_embed_rgb8(x.data_ptr(), x.data_ptr(), 1, 16, 16, 768, m.data_ptr(), 1, 0.1, 3, 0, None) == -2
     with pytest.raises(ValueError, match="watermark map"):
         W.embed_tensor(x, torch.zeros((3, 2), dtype=torch.uint8, device="cuda"))
     with pytest.raises(ValueError, match="same shape"):
@@ -416,3 +419,44 @@ def test_qr_payload_bit_exact_through_the_drop_in_api(mode):
     assert_pixels(np.array(out), ref, what="1080p QR embed")
     assert_extract(np.array(W.extract_watermark(Image.fromarray(ref), img, custom_settings=s)), ref_ext, "1080p QR extract")
     assert Q.decode_map(O.extract_array(np.array(out), rgb)) == got       # reference extractor on the GPU's image
+
+
+# --------------------------------------------------------------------------- the UI's other block sizes
+@pytest.mark.parametrize("name", BS_CASES)
+def test_other_block_sizes_against_reference_vectors(golden, name):
+    g = golden(name)
+    bs, alpha = int(g["bs"]), float(g["alpha"])
+    x = torch.from_numpy(g["rgb"]).cuda()
+    out = W.embed_tensor(x, torch.from_numpy(g["wm"]).cuda(), alpha, bs).cpu().numpy()
+    assert np.abs(out.astype(int) - g["ref_out"].astype(int)).max() <= 1
+    ext = W.extract_tensor(torch.from_numpy(g["ref_out"]).cuda(), x, alpha, bs).cpu().numpy()
+    assert_extract(ext, g["ref_ext"], name)
+    s = {"block_size": bs, "alpha": alpha}
+    pil = W.embed_watermark(Image.fromarray(g["rgb"]), Image.fromarray(g["wm"]), False, s)
+    assert np.array_equal(np.array(pil), out)
+    e2 = W.extract_watermark(Image.fromarray(g["ref_out"]), Image.fromarray(g["rgb"]), s)
+    assert e2.size == (g["wm"].shape[1], g["wm"].shape[0]) and np.array_equal(np.array(e2), ext)
+
+
+@pytest.mark.parametrize("bs", [4, 6, 10, 12, 14, 16])
+def test_other_block_sizes_vs_oracle(bs):
+    rng = np.random.default_rng(bs)
+    for (h, w) in ((7 * bs + 1, 9 * bs + 3), (16 * bs, 24 * bs)):          # ragged / aligned
+        img = natural_like(h, w, bs)
+        wm = np.where(rng.random((h // bs, w // bs)) < 0.4, 0, rng.integers(1, 256, (h // bs, w // bs))).astype(np.uint8)
+        ref = O.embed_array(img, wm, 0.1, bs)
+        x = torch.from_numpy(img).cuda()
+        out = W.embed_tensor(x, torch.from_numpy(wm).cuda(), 0.1, bs).cpu().numpy()
+        assert np.abs(out.astype(int) - ref.astype(int)).max() <= 1, (bs, h, w)
+        assert_extract(W.extract_tensor(torch.from_numpy(ref).cuda(), x, 0.1, bs).cpu().numpy(),
+                       O.extract_array(ref, img, 0.1, bs), f"bs {bs}")
+        s0 = W.sigma0_tensor(x, bs).cpu().numpy()
+        Y = O.rgb_to_ycbcr(img)[:, :, 0]
+        sref = np.linalg.svd(O.to_blocks(Y, bs).astype(np.float64), compute_uv=False)[..., 0]
+        assert (np.abs(s0 - sref) <= SIGMA_RTOL * sref + 1e-12).all()
+    # batch path with per-image maps
+    imgs = np.stack([natural_like(4 * bs, 6 * bs, k) for k in range(3)])
+    wms = rng.integers(0, 256, (3, 4, 6), dtype=np.uint8)
+    got = W.embed_watermark_batch(imgs, wms, 0.1, bs)
+    for k in range(3):
+        assert np.abs(got[k].astype(int) - O.embed_array(imgs[k], wms[k], 0.1, bs).astype(int)).max() <= 1

@@ -38,8 +38,10 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_argument_validation_happens_before_any_cuda_work(lib):
     # these return from the host-side checks, so they are safe without a GPU
-    assert lib.tmf_embed_rgb8(None, None, 1, 16, 16, 16 * 16 * 3, None, 1, 0.1, 4, 0, None) == -2
-    assert "block_size 4 is not supported" in _lib.last_error()
+    assert lib.tmf_embed_rgb8(None, None, 1, 16, 16, 16 * 16 * 3, None, 1, 0.1, 5, 0, None) == -2
+    assert "block_size 5 is not supported" in _lib.last_error()
+    assert lib.tmf_embed_rgb8(None, None, 1, 16, 16, 16 * 16 * 3, None, 1, 0.1, 18, 0, None) == -2
+    assert lib.tmf_embed_rgb8(None, None, 1, 16, 16, 16 * 16 * 3, None, 1, 0.1, 4, 0, None) == -1   # supported size, null pointers
     assert lib.tmf_embed_rgb8(None, None, 1, 16, 16, 16 * 16 * 3, None, 1, 0.1, 8, 0, None) == -1
     assert lib.tmf_embed_rgb8(None, None, 1, 16, 16, 10, None, 1, 0.1, 8, 0, None) == -1
     assert "img_stride" in _lib.last_error()

@@ -10,7 +10,8 @@ from conftest import golden_names
 from oracle import wm_oracle as O
 from oracle.make_golden import natural_like, regions
 
-ARRAY_CASES = [n for n in golden_names() if not n.startswith("pil_") and n != "subblock_5x7"]
+ARRAY_CASES = [n for n in golden_names() if not n.startswith(("pil_", "bs")) and n != "subblock_5x7"]
+BS_CASES = [n for n in golden_names() if n.startswith("bs")]
 
 
 def _tie(S, rel=1e-4):
@@ -134,3 +135,35 @@ def test_qr_payload_survives_embed_extract(mode):
     # cross paths decode to the same bytes
     assert Q.decode_map(O.extract_array(out, c["rgb"])) == ref_payload
     assert Q.decode_map(H.extract(c["ref"], c["rgb"], mode=mode)) == ref_payload
+
+
+@pytest.mark.parametrize("bs", [4, 6, 10, 12, 14, 16])
+def test_other_block_sizes_math_vs_oracle(bs):
+    """the UI's other block sizes (embed_watermark_page.py:324-331)."""
+    rng = np.random.default_rng(bs)
+    img = natural_like(7 * bs + 1, 9 * bs + 3, bs)            # ragged: strips on both sides
+    wm = np.where(rng.random((7, 9)) < 0.4, 0, rng.integers(1, 256, (7, 9))).astype(np.uint8)
+    for alpha in (0.1, 0.6):
+        taps = {}
+        ref = O.embed_array(img, wm, alpha, bs, taps=taps)
+        out = H.embed_n(img, wm, alpha, bs)
+        d = np.abs(out.astype(int) - ref.astype(int))
+        assert d.max() <= 1, (bs, alpha, d.max())
+        rext = O.extract_array(ref, img, alpha, bs)
+        ext = H.extract_n(ref, img, alpha, bs)
+        assert np.abs(ext.astype(int) - rext.astype(int)).max() <= 1
+        decided = np.abs(rext.astype(int) - 128) > 1
+        assert np.array_equal((ext >= 128)[decided], (rext >= 128)[decided])
+    flat = np.zeros((2 * bs, 2 * bs, 3), np.uint8)              # sigma0 = 0: mark lands on DC
+    wmf = np.full((2, 2), 255, np.uint8)
+    assert np.abs(H.embed_n(flat, wmf, 0.1, bs).astype(int) - O.embed_array(flat, wmf, 0.1, bs).astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("name", BS_CASES)
+def test_other_block_sizes_math_vs_reference_vectors(golden, name):
+    g = golden(name)
+    bs, alpha = int(g["bs"]), float(g["alpha"])
+    out = H.embed_n(g["rgb"], g["wm"], alpha, bs)
+    assert np.abs(out.astype(int) - g["ref_out"].astype(int)).max() <= 1
+    ext = H.extract_n(g["ref_out"], g["rgb"], alpha, bs)
+    assert np.abs(ext.astype(int) - g["ref_ext"].astype(int)).max() <= 1

@@ -13,7 +13,8 @@ from PIL import Image
 from conftest import GOLDEN_DIR, golden_names
 from oracle import live_reference, wm_oracle as O
 
-ARRAY_CASES = [n for n in golden_names() if not n.startswith("pil_")]
+ARRAY_CASES = [n for n in golden_names() if not n.startswith(("pil_", "bs"))]
+BS_CASES = [n for n in golden_names() if n.startswith("bs")]
 
 
 def _sha(a):
@@ -29,6 +30,14 @@ def test_oracle_embed_extract_matches_reference_vectors(golden, name):
         ext = O.extract_array(g["ref_out"], g["rgb"], 0.1, 8)
         assert np.array_equal(ext, g["ref_ext"])
     assert np.array_equal(O.rgb_to_ycbcr(g["rgb"]), g["ref_ycc"])
+
+
+@pytest.mark.parametrize("name", BS_CASES)
+def test_oracle_other_block_sizes_match_reference_vectors(golden, name):
+    g = golden(name)
+    bs, alpha = int(g["bs"]), float(g["alpha"])
+    assert np.array_equal(O.embed_array(g["rgb"], g["wm"], alpha, bs), g["ref_out"])
+    assert np.array_equal(O.extract_array(g["ref_out"], g["rgb"], alpha, bs), g["ref_ext"])
 
 
 @pytest.mark.parametrize("name", ["gv1_random64", "natural_ragged_70x93", "flat_black16"])

@@ -38,61 +38,72 @@
 namespace tmf {
 
 
-// upper triangle of a symmetric 8x8 in 36 registers: index of (i, j), i <= j
-#define TMF_SYM(i, j) ((i) * 8 - ((i) * ((i) + 1)) / 2 + (j))
-#define TMF_SYMG(m, i, j) ((m)[((i) <= (j)) ? TMF_SYM(i, j) : TMF_SYM(j, i)])
+// upper triangle of a symmetric NxN in N(N+1)/2 registers: index of (i, j), any order.
+// N = 8 is the reference's BLOCK_SIZE; the templates also serve the other sizes its UI
+// offers (4..16, embed_watermark_page.py:324-331).
+template <int N>
+TMF_HD constexpr int sym_idx(int i, int j) {
+  return (i <= j) ? (i * N - (i * (i + 1)) / 2 + j) : (j * N - (j * (j + 1)) / 2 + i);
+}
+#define TMF_SYM(i, j) (tmf::sym_idx<8>((i), (j)))
 
-// pass 1: G += y^T y for one row y[8] of the block
+// pass 1: G += y^T y for one row y[N] of the block
+template <int N = 8>
 TMF_HD void gram_accumulate_row(const float* y, float* g) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < N; ++i)
 #pragma unroll
-    for (int j = i; j < 8; ++j) g[TMF_SYM(i, j)] = fmaf(y[i], y[j], g[TMF_SYM(i, j)]);
+    for (int j = i; j < N; ++j) g[sym_idx<N>(i, j)] = fmaf(y[i], y[j], g[sym_idx<N>(i, j)]);
 }
 
+template <int N = 8>
 TMF_HD float sym_trace(const float* g) {
   float tr = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) tr += g[TMF_SYM(i, i)];
+  for (int i = 0; i < N; ++i) tr += g[sym_idx<N>(i, i)];
   return tr;
 }
 
 // p = m * m for symmetric m (upper triangles); returns tr(p)
+template <int N = 8>
 TMF_HD float sym_square(const float* m, float* p) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < N; ++i)
 #pragma unroll
-    for (int j = i; j < 8; ++j) {
+    for (int j = i; j < N; ++j) {
       float s = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) s = fmaf(TMF_SYMG(m, i, k), TMF_SYMG(m, k, j), s);
-      p[TMF_SYM(i, j)] = s;
+      for (int k = 0; k < N; ++k) s = fmaf(m[sym_idx<N>(i, k)], m[sym_idx<N>(k, j)], s);
+      p[sym_idx<N>(i, j)] = s;
     }
-  return sym_trace(p);
+  return sym_trace<N>(p);
 }
 
 // y = M x for symmetric M (upper triangle)
+template <int N = 8>
 TMF_HD void sym_matvec(const float* m, const float* x, float* y) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < N; ++i) {
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s = fmaf(TMF_SYMG(m, i, j), x[j], s);
+    for (int j = 0; j < N; ++j) s = fmaf(m[sym_idx<N>(i, j)], x[j], s);
     y[i] = s;
   }
 }
 
-TMF_HD float dot8(const float* a, const float* b) {
+template <int N = 8>
+TMF_HD float dotn(const float* a, const float* b) {
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s = fmaf(a[i], b[i], s);
+  for (int i = 0; i < N; ++i) s = fmaf(a[i], b[i], s);
   return s;
 }
+TMF_HD float dot8(const float* a, const float* b) { return dotn<8>(a, b); }
 
 // Top eigenpair of the unit-trace Gram matrix m (entrywise >= 0; DESTROYED) of a
 // luma block: certified power iteration with adaptive squaring.
 //
-//   level 0: v = 1 (tan(angle to v0) <= sqrt7 by Perron-Frobenius), x = M v, y = M x.
+//   level 0: v = 1 (tan(angle to v0) <= sqrt(N-1) by Perron-Frobenius), x = M v, y = M x.
 //   The Rayleigh quotient of x gives rho^ = (1 - mu^)/mu^ >= mu_1/mu_0 (unit trace), so
 //   tan(angle(y)) <= theta * rho^^2, and every further product multiplies the bound by
 //   rho^.  If at most 3 more products reach the tolerance, do them and stop.
@@ -107,22 +118,24 @@ TMF_HD float dot8(const float* a, const float* b) {
 #define TMF_FAST_TOL_VEC_EXTRACT 3.0e-4f   // sigma0 only: second order in the vector error
 #define TMF_FAST_MAX_LEVELS 18
 
-template <bool EMBED>
+template <bool EMBED, int N = 8>
 TMF_HD int top_pair(float* m, float* w, float& ww, float& mu) {
+  constexpr int NS = N * (N + 1) / 2;
   const float tol = EMBED ? TMF_FAST_TOL_VEC_EMBED : TMF_FAST_TOL_VEC_EXTRACT;
-  float x[8], y[8], tr2[TMF_FAST_MAX_LEVELS];
-  float theta = 2.6457513f;              // sqrt(7)
+  const float theta0 = f_sqrt((float)(N - 1));
+  float x[N], y[N], tr2[TMF_FAST_MAX_LEVELS];
+  float theta = theta0;
   int level = 0, products = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) y[i] = 1.0f;
+  for (int i = 0; i < N; ++i) y[i] = 1.0f;
   float xy, yy;
   for (;;) {
-    sym_matvec(m, y, x);                 // x = M v      (v is y from the previous level, or ones)
-    sym_matvec(m, x, y);                 // y = M x
+    sym_matvec<N>(m, y, x);              // x = M v      (v is y from the previous level, or ones)
+    sym_matvec<N>(m, x, y);              // y = M x
     products += 2;
-    const float xx = dot8(x, x);
-    xy = dot8(x, y);
-    yy = dot8(y, y);
+    const float xx = dotn<N>(x, x);
+    xy = dotn<N>(x, y);
+    yy = dotn<N>(y, y);
     const float rho = fmaxf(xx - xy, 0.0f) * f_rcp_fast(xy);
     float err = theta * rho * rho;       // bound on tan(angle(y, v0))
     int more = 0;
@@ -134,32 +147,32 @@ TMF_HD int top_pair(float* m, float* w, float& ww, float& mu) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         if (k < more) {
-          sym_matvec(m, y, x);           // x = M y
-          xy = dot8(y, x);               // w_{J-1}.w_J
-          yy = dot8(x, x);               // w_J.w_J
+          sym_matvec<N>(m, y, x);        // x = M y
+          xy = dotn<N>(y, x);            // w_{J-1}.w_J
+          yy = dotn<N>(x, x);            // w_J.w_J
 #pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = x[i];
+          for (int i = 0; i < N; ++i) y[i] = x[i];
         }
       }
       products += more;
       break;
     }
     // square in place: M <- M^2 / tr(M^2)
-    float p[36];
-    const float t = sym_square(m, p);
+    float p[NS];
+    const float t = sym_square<N>(m, p);
     tr2[level] = t;
     const float inv = f_rcp_fast(t);
 #pragma unroll
-    for (int k = 0; k < 36; ++k) m[k] = p[k] * inv;
+    for (int k = 0; k < NS; ++k) m[k] = p[k] * inv;
     // carry y over as the next start vector, rescaled so nothing underflows
     const float rn = f_rsqrt(yy);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] *= rn;
-    theta = fminf(theta * rho * rho, 2.6457513f);
+    for (int i = 0; i < N; ++i) y[i] *= rn;
+    theta = fminf(theta * rho * rho, theta0);
     ++level;
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) w[i] = y[i];
+  for (int i = 0; i < N; ++i) w[i] = y[i];
   ww = yy;
   mu = yy * f_rcp_fast(xy);              // (w_J.w_J)/(w_{J-1}.w_J) <= mu_0 of the current level
   for (int l = level - 1; l >= 0; --l) mu = f_sqrt(mu * tr2[l]);
@@ -168,45 +181,49 @@ TMF_HD int top_pair(float* m, float* w, float& ww, float& mu) {
 
 // Per-block scalars of the embed, from the Gram matrix accumulated in pass 1
 // (g in 0..255 units, destroyed).  Output for pass 2:
-//   w[8], and  y'_ij = y_ij + (f * z_i + c) * w_j,  z_i = row_i . w
-// with (f, c) = (d255 / (sigma255 w.w), 0), or (0, d255/8) with w = 1 for an
+//   w[N], and  y'_ij = y_ij + (f * z_i + c) * w_j,  z_i = row_i . w
+// with (f, c) = (d255 / (sigma255 w.w), 0), or (0, d255/N) with w = 1 for an
 // all-zero block (LAPACK's U = V = I puts the mark on the DC coefficient, which
-// is the constant 1/8 pattern in the spatial domain).  Returns sigma0 in the
+// is the constant 1/N pattern in the spatial domain).  Returns sigma0 in the
 // reference's units (luma in [0, 1]).
+template <int N = 8>
 TMF_HD float embed_block_scalars_fast(float* g, double alpha, uint32_t wm_u8, float* w, float& f, float& c,
                                       int* iters) {
-  const float tr = sym_trace(g);
-  float sig255 = 0.0f, ww = 8.0f;
+  constexpr int NS = N * (N + 1) / 2;
+  const float tr = sym_trace<N>(g);
+  float sig255 = 0.0f, ww = (float)N;
   if (tr > 0.0f) {
     const float inv = f_rcp_fast(tr);
 #pragma unroll
-    for (int k = 0; k < 36; ++k) g[k] *= inv;
+    for (int k = 0; k < NS; ++k) g[k] *= inv;
     float mu;
-    const int it = top_pair<true>(g, w, ww, mu);
+    const int it = top_pair<true, N>(g, w, ww, mu);
     if (iters) *iters = it;
     sig255 = f_sqrt(tr * mu);
   } else {
     if (iters) *iters = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = 1.0f;
+    for (int i = 0; i < N; ++i) w[i] = 1.0f;
   }
   const float sig = sig255 * (1.0f / 255.0f);
   const float d255 = (modulate_sigma0(sig, alpha, wm_u8) - sig) * 255.0f;   // watermarking.py:198
   if (tr > 0.0f) { f = f_div(d255, sig255 * ww); c = 0.0f; }
-  else { f = 0.0f; c = d255 * 0.125f; }
+  else { f = 0.0f; c = d255 * (1.0f / (float)N); }
   return sig;
 }
 
 // Largest singular value (reference units) from the pass-1 Gram matrix (destroyed).
+template <int N = 8>
 TMF_HD float sigma0_from_gram_fast(float* g, int* iters) {
-  const float tr = sym_trace(g);
+  constexpr int NS = N * (N + 1) / 2;
+  const float tr = sym_trace<N>(g);
   if (iters) *iters = 0;
   if (!(tr > 0.0f)) return 0.0f;
   const float inv = f_rcp_fast(tr);
 #pragma unroll
-  for (int k = 0; k < 36; ++k) g[k] *= inv;
-  float w[8], ww, mu;
-  const int it = top_pair<false>(g, w, ww, mu);
+  for (int k = 0; k < NS; ++k) g[k] *= inv;
+  float w[N], ww, mu;
+  const int it = top_pair<false, N>(g, w, ww, mu);
   if (iters) *iters = it;
   return f_sqrt(tr * mu) * (1.0f / 255.0f);
 }
@@ -255,12 +272,13 @@ TMF_HD uint32_t pack4_sat_u8(int a0, int a1, int a2, int a3) {
 }
 
 // pass 2 for one row: r, g, b in 0..255 units and the row's luma y (kept from
-// pass 1) -> 24 output levels q[3j + c] (unclipped floors; pack4_sat_u8 clips)
+// pass 1) -> 3N output levels q[3j + c] (unclipped floors; pack4_sat_u8 clips)
+template <int N = 8>
 TMF_HD void embed_row_fast(const float* r, const float* g, const float* b, const float* y, const float* w, float f,
                            float c, int* q) {
-  const float du = fmaf(f, dot8(y, w), c);
+  const float du = fmaf(f, dotn<N>(y, w), c);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < N; ++j) {
     float R, G, B;
     rgb255_out_fast(r[j], g[j], b[j], du * w[j], R, G, B);
     q[3 * j] = floor_to_int(R);

@@ -90,6 +90,7 @@ __device__ __forceinline__ void store_row24(uint8_t* __restrict__ p, const uint3
 
 struct BlockGeom {
   int h, w, nbh, nbw;
+  int bs;                     // block size (8 on the optimised path)
   long long blocks_per_img;   // nbh * nbw
   long long total_blocks;     // n * blocks_per_img
   size_t img_stride;          // bytes between images
@@ -196,7 +197,7 @@ k_strip_roundtrip(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, Bl
   if (t >= strip_px_per_img * n) return;
   const long long img = t / strip_px_per_img;
   long long idx = t - img * strip_px_per_img;
-  const int bw = g.nbw * 8, bh = g.nbh * 8, rw = g.w - bw;
+  const int bw = g.nbw * g.bs, bh = g.nbh * g.bs, rw = g.w - bw;
   int y, x;
   if (idx < (long long)g.h * rw) {
     y = (int)(idx / rw);
@@ -408,6 +409,123 @@ k_sigma0_fast(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, Block
   sigma0[gb] = tmf::sigma0_from_gram_fast(gm, nullptr);
 }
 
+
+// ---------------------------------------------------------------------------
+// Other block sizes of the reference's UI (embed_watermark_page.py:324-331: 4..16,
+// even).  Same streaming algebra (tmf_fast.cuh is templated on N), one thread per
+// block, plain 32-bit or byte accesses; correctness first - the tuned path is N = 8.
+// Both `mode`s take this path for N != 8.
+// ---------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ size_t block_origin_n(const BlockGeom& g, long long gb, long long& img, int& by, int& bx) {
+  img = gb / g.blocks_per_img;
+  const int r = (int)(gb - img * g.blocks_per_img);
+  by = r / g.nbw;
+  bx = r - by * g.nbw;
+  return (size_t)img * g.img_stride + (size_t)by * N * g.row_pitch + (size_t)bx * (3 * N);
+}
+
+template <int N, bool AL4>
+__device__ __forceinline__ void load_row_rgb255_n(const uint8_t* __restrict__ p, float* r, float* g, float* b) {
+  uint8_t raw[3 * N];
+  if (AL4) {
+#pragma unroll
+    for (int k = 0; k < (3 * N) / 4; ++k) {
+      const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p) + k);
+      raw[4 * k] = (uint8_t)w; raw[4 * k + 1] = (uint8_t)(w >> 8); raw[4 * k + 2] = (uint8_t)(w >> 16); raw[4 * k + 3] = (uint8_t)(w >> 24);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3 * N; ++k) raw[k] = __ldg(p + k);
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) { r[j] = (float)raw[3 * j]; g[j] = (float)raw[3 * j + 1]; b[j] = (float)raw[3 * j + 2]; }
+}
+
+template <int N, bool AL4>
+__device__ __forceinline__ void gram_of_block_n(const uint8_t* __restrict__ base, size_t pitch, float* gm) {
+#pragma unroll
+  for (int k = 0; k < N * (N + 1) / 2; ++k) gm[k] = 0.0f;
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) {
+    float r[N], g[N], b[N], y[N];
+    load_row_rgb255_n<N, AL4>(base + (size_t)i * pitch, r, g, b);
+#pragma unroll
+    for (int j = 0; j < N; ++j) y[j] = tmf::luma255_fast(r[j], g[j], b[j]);
+    tmf::gram_accumulate_row<N>(y, gm);
+  }
+}
+
+template <int N, bool AL4>
+__global__ void __launch_bounds__(kThreads)
+k_embed_fast_n(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGeom g,
+               const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
+  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (gb >= g.total_blocks) return;
+  long long img; int by, bx;
+  const size_t org = block_origin_n<N>(g, gb, img, by, bx);
+  const uint8_t* src = rgb + org;
+  uint8_t* dst = out + org;
+  const long long wi = (wm_shared ? 0 : img * g.blocks_per_img) + (long long)by * g.nbw + bx;
+  const uint32_t mark = (uint32_t)__ldg(wm + wi);
+  float w[N], f = 0.0f, c = 0.0f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) w[i] = 0.0f;
+  if (mark != 0) {
+    float gm[N * (N + 1) / 2];
+    gram_of_block_n<N, AL4>(src, g.row_pitch, gm);
+    tmf::embed_block_scalars_fast<N>(gm, alpha, mark, w, f, c, nullptr);
+  }
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) {
+    float r[N], gg[N], b[N], y[N];
+    int q[3 * N];
+    load_row_rgb255_n<N, AL4>(src + (size_t)i * g.row_pitch, r, gg, b);
+#pragma unroll
+    for (int j = 0; j < N; ++j) y[j] = tmf::luma255_fast(r[j], gg[j], b[j]);
+    tmf::embed_row_fast<N>(r, gg, b, y, w, f, c, q);
+    uint8_t* d = dst + (size_t)i * g.row_pitch;
+    if (AL4) {
+#pragma unroll
+      for (int k = 0; k < (3 * N) / 4; ++k)
+        reinterpret_cast<uint32_t*>(d)[k] = tmf::pack4_sat_u8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3 * N; ++k) d[k] = (uint8_t)min(max(q[k], 0), 255);
+    }
+  }
+}
+
+template <int N, bool AL4>
+__device__ __forceinline__ float sigma0_of_block_n(const uint8_t* __restrict__ base, size_t pitch) {
+  float gm[N * (N + 1) / 2];
+  gram_of_block_n<N, AL4>(base, pitch, gm);
+  return tmf::sigma0_from_gram_fast<N>(gm, nullptr);
+}
+
+template <int N, bool AL4>
+__global__ void __launch_bounds__(kThreads)
+k_extract_fast_n(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ orig, uint8_t* __restrict__ out_wm,
+                 BlockGeom g, double alpha) {
+  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (gb >= g.total_blocks) return;
+  long long img; int by, bx;
+  const size_t org = block_origin_n<N>(g, gb, img, by, bx);
+  const float sw = sigma0_of_block_n<N, AL4>(wmk + org, g.row_pitch);
+  const float so = sigma0_of_block_n<N, AL4>(orig + org, g.row_pitch);
+  out_wm[gb] = (uint8_t)tmf::extract_level(sw, so, alpha);
+}
+
+template <int N, bool AL4>
+__global__ void __launch_bounds__(kThreads)
+k_sigma0_fast_n(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, BlockGeom g) {
+  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (gb >= g.total_blocks) return;
+  long long img; int by, bx;
+  const size_t org = block_origin_n<N>(g, gb, img, by, bx);
+  sigma0[gb] = sigma0_of_block_n<N, AL4>(rgb + org, g.row_pitch);
+}
+
 // ---------------------------------------------------------------------------
 // standalone batched SVD / DCT / colour taps
 // ---------------------------------------------------------------------------
@@ -602,14 +720,14 @@ k_ycc2rgb(const float* __restrict__ ycc, uint8_t* __restrict__ rgb, long long np
 // host-side helpers
 // ---------------------------------------------------------------------------
 int make_geom(int n, int h, int w, size_t img_stride, int block, BlockGeom& g) {
-  if (block != 8)
+  if (block < 4 || block > 16 || (block & 1))
     return fail(TMF_ERR_UNSUPPORTED_BLOCK,
-                "block_size %d is not supported: this build implements the reference's BLOCK_SIZE = 8 only "
-                "(there is no CPU fallback)", block);
+                "block_size %d is not supported: this build implements the even sizes 4..16 the reference's UI "
+                "offers (8, its BLOCK_SIZE, on the optimised path); there is no CPU fallback", block);
   if (n < 0 || h < 0 || w < 0) return fail(TMF_ERR_BAD_ARG, "negative dimension (n=%d h=%d w=%d)", n, h, w);
   if (n > 0 && img_stride < (size_t)h * w * 3)
     return fail(TMF_ERR_BAD_ARG, "img_stride %zu is smaller than one image (%zu bytes)", img_stride, (size_t)h * w * 3);
-  g.h = h; g.w = w; g.nbh = h / 8; g.nbw = w / 8;
+  g.h = h; g.w = w; g.bs = block; g.nbh = h / block; g.nbw = w / block;
   g.blocks_per_img = (long long)g.nbh * g.nbw;
   g.total_blocks = g.blocks_per_img * n;
   g.img_stride = img_stride;
@@ -625,6 +743,24 @@ int pick_vec(const BlockGeom& g, const void* p0, const void* p1, const void* p2 
 }
 
 unsigned grid_for(long long items, int per_cta) { return (unsigned)((items + per_cta - 1) / per_cta); }
+
+
+// dispatch over the block sizes other than 8
+#define TMF_FOR_N(N_, AL4_, CALL)                          \
+  switch (N_) {                                            \
+    case 4:  { constexpr int N = 4;  if (AL4_) { constexpr bool A = true; CALL; } else { constexpr bool A = false; CALL; } } break; \
+    case 6:  { constexpr int N = 6;  constexpr bool A = false; CALL; } break;   /* 18-byte rows: never 4-byte aligned per block */ \
+    case 10: { constexpr int N = 10; constexpr bool A = false; CALL; } break;  \
+    case 12: { constexpr int N = 12; if (AL4_) { constexpr bool A = true; CALL; } else { constexpr bool A = false; CALL; } } break; \
+    case 14: { constexpr int N = 14; constexpr bool A = false; CALL; } break;  \
+    case 16: { constexpr int N = 16; if (AL4_) { constexpr bool A = true; CALL; } else { constexpr bool A = false; CALL; } } break; \
+    default: break;                                        \
+  }
+
+bool aligned4(const BlockGeom& g, const void* p0, const void* p1, const void* p2 = nullptr) {
+  uintptr_t bits = (uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2 | (uintptr_t)g.img_stride | (uintptr_t)g.row_pitch;
+  return (bits & 3) == 0;
+}
 
 }  // namespace
 
@@ -654,7 +790,12 @@ int tmf_embed_rgb8(const uint8_t* rgb, uint8_t* out, int n, int h, int w, size_t
   if (g.total_blocks > 0 && !wm) return fail(TMF_ERR_BAD_ARG, "null watermark map");
   if (!(alpha == alpha)) return fail(TMF_ERR_BAD_ARG, "alpha is NaN");
   cudaStream_t st = (cudaStream_t)stream;
-  if (g.total_blocks > 0) {
+  if (g.total_blocks > 0 && block != 8) {
+    const unsigned grid = grid_for(g.total_blocks, kThreads);
+    const bool al4 = aligned4(g, rgb, out);
+    TMF_FOR_N(block, al4, (k_embed_fast_n<N, A><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha)));
+    if (int rc = check_launch("embed kernel launch")) return rc;
+  } else if (g.total_blocks > 0) {
     const unsigned grid = grid_for(g.total_blocks, kThreads);
     const int vec = pick_vec(g, rgb, out);
     if (mode == TMF_MODE_FAST) {
@@ -672,7 +813,7 @@ int tmf_embed_rgb8(const uint8_t* rgb, uint8_t* out, int n, int h, int w, size_t
     }
     if (int rc = check_launch("embed kernel launch")) return rc;
   }
-  const long long strip = (long long)h * w - g.blocks_per_img * 64;
+  const long long strip = (long long)h * w - g.blocks_per_img * block * block;
   if (strip > 0) {
     k_strip_roundtrip<<<grid_for(strip * n, 256), 256, 0, st>>>(rgb, out, g, n, strip);
     if (int rc = check_launch("strip kernel launch")) return rc;
@@ -690,6 +831,11 @@ int tmf_extract_rgb8(const uint8_t* wmk_rgb, const uint8_t* orig_rgb, uint8_t* o
   if (!(alpha == alpha) || alpha == 0.0) return fail(TMF_ERR_BAD_ARG, "alpha must be a non-zero number");
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = grid_for(g.total_blocks, kThreads);
+  if (block != 8) {
+    const bool al4 = aligned4(g, wmk_rgb, orig_rgb);
+    TMF_FOR_N(block, al4, (k_extract_fast_n<N, A><<<grid, kThreads, 0, st>>>(wmk_rgb, orig_rgb, out_wm, g, alpha)));
+    return check_launch("extract kernel launch");
+  }
   const int vec = pick_vec(g, wmk_rgb, orig_rgb);
   if (mode == TMF_MODE_FAST) {
     switch (vec) {
@@ -716,6 +862,11 @@ int tmf_sigma0_rgb8(const uint8_t* rgb, float* sigma0, int n, int h, int w, size
   if (!rgb || !sigma0) return fail(TMF_ERR_BAD_ARG, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = grid_for(g.total_blocks, kThreads);
+  if (block != 8) {
+    const bool al4 = aligned4(g, rgb, rgb);
+    TMF_FOR_N(block, al4, (k_sigma0_fast_n<N, A><<<grid, kThreads, 0, st>>>(rgb, sigma0, g)));
+    return check_launch("sigma0 kernel launch");
+  }
   const int vec = pick_vec(g, rgb, rgb);
   if (mode == TMF_MODE_FAST) {
     switch (vec) {

@@ -24,7 +24,8 @@ DEFAULT_CHUNK_BYTES = 96 << 20
 class HostPipeline:
     """Chunked, stream-overlapped embed/extract for one device and one image size."""
 
-    def __init__(self, device: int, h: int, w: int, chunk_images: int, kind: str, depth: int = 2):
+    def __init__(self, device: int, h: int, w: int, chunk_images: int, kind: str, depth: int = 2,
+                 block_size: int = BLOCK_SIZE):
         from . import watermarking as wmk
 
         torch = wmk._torch()
@@ -33,7 +34,7 @@ class HostPipeline:
         self.torch, self.kind, self.h, self.w = torch, kind, h, w
         self.device = torch.device("cuda", device)
         self.chunk, self.depth = max(1, int(chunk_images)), max(1, int(depth))
-        nbh, nbw = h // 8, w // 8
+        nbh, nbw = h // block_size, w // block_size
         with torch.cuda.device(self.device):
             self.s_in, self.s_run, self.s_out = (torch.cuda.Stream() for _ in range(3))
             mk = lambda *shape: torch.empty(shape, dtype=torch.uint8, device=self.device)
@@ -129,12 +130,12 @@ def run_batch(kind, a, b, wm_map, alpha=ALPHA, block_size=BLOCK_SIZE, mode=None,
     from . import watermarking as wmk
 
     torch = wmk._torch()
-    wmk._require_block8(block_size)
+    block_size = wmk._require_supported_block(block_size)
     ta, flavour = _as_cpu_u8(a, "images")
     if ta.dim() != 4 or ta.shape[-1] != 3:
         raise ValueError(f"images must have shape (N, H, W, 3), got {tuple(ta.shape)}")
     n, h, w, _ = ta.shape
-    nbh, nbw = h // 8, w // 8
+    nbh, nbw = h // block_size, w // block_size
     tb = None
     if kind == "extract":
         tb, _ = _as_cpu_u8(b, "originals")
@@ -165,7 +166,7 @@ def run_batch(kind, a, b, wm_map, alpha=ALPHA, block_size=BLOCK_SIZE, mode=None,
     for dev, (lo, hi) in zip(devices, shard_ranges(n, len(devices))):
         if hi <= lo:
             continue
-        p = HostPipeline(dev, h, w, min(chunk, hi - lo), kind)
+        p = HostPipeline(dev, h, w, min(chunk, hi - lo), kind, block_size=block_size)
         pipes.append(p)
         if kind == "embed" and tw.dim() == 2:
             wms.append(tw.to(p.device))          # shared map: resident before the first launch

@@ -115,14 +115,17 @@ def embed_tensor(rgb, wm, alpha=ALPHA, block_size=BLOCK_SIZE, mode=None, out=Non
     """Fused embed on device-resident images.
 
     ``rgb``: CUDA uint8 ``(N, H, W, 3)`` (or ``(H, W, 3)``).  ``wm``: CUDA uint8
-    watermark map ``(H//8, W//8)`` shared by the batch, or ``(N, H//8, W//8)``.
+    watermark map ``(H//bs, W//bs)`` shared by the batch, or ``(N, H//bs, W//bs)``
+    (``bs`` = ``block_size``: 8 is the tuned path, the other even sizes 4..16 run a
+    generic kernel).
     Returns a CUDA uint8 tensor shaped like ``rgb``.  Asynchronous on the current
     stream."""
     torch = _torch()
     squeeze = rgb.dim() == 3
     x = _check_u8_images(rgb, "rgb")
     n, h, w, _ = x.shape
-    nbh, nbw = h // 8, w // 8
+    bs = _require_supported_block(block_size)
+    nbh, nbw = h // bs, w // bs
     if not (isinstance(wm, torch.Tensor) and wm.is_cuda and wm.dtype == torch.uint8):
         raise ValueError("wm must be a CUDA uint8 tensor")
     wm = wm.contiguous()
@@ -158,14 +161,15 @@ def extract_tensor(wmk, orig, alpha=ALPHA, block_size=BLOCK_SIZE, mode=None, out
     if a.device != b.device:
         raise ValueError("watermarked and original images must be on the same device")
     n, h, w, _ = a.shape
+    bs = _require_supported_block(block_size)
     if out is None:
-        out = torch.empty((n, h // 8, w // 8), dtype=torch.uint8, device=a.device)
+        out = torch.empty((n, h // bs, w // bs), dtype=torch.uint8, device=a.device)
     else:
         if out.dim() == 2:
             out = out.unsqueeze(0)
-        if (tuple(out.shape) != (n, h // 8, w // 8) or out.dtype != torch.uint8 or not out.is_cuda
+        if (tuple(out.shape) != (n, h // bs, w // bs) or out.dtype != torch.uint8 or not out.is_cuda
                 or not out.is_contiguous()):
-            raise ValueError(f"out must be a contiguous CUDA uint8 tensor of shape {(n, h // 8, w // 8)}")
+            raise ValueError(f"out must be a contiguous CUDA uint8 tensor of shape {(n, h // bs, w // bs)}")
     lib = _lib.load()
     with torch.cuda.device(a.device):
         _lib.check(lib.tmf_extract_rgb8(a.data_ptr(), b.data_ptr(), out.data_ptr(), n, h, w, h * w * 3,
@@ -180,7 +184,8 @@ def sigma0_tensor(rgb, block_size=BLOCK_SIZE, mode=None):
     squeeze = rgb.dim() == 3
     x = _check_u8_images(rgb, "rgb")
     n, h, w, _ = x.shape
-    out = torch.empty((n, h // 8, w // 8), dtype=torch.float32, device=x.device)
+    bs = _require_supported_block(block_size)
+    out = torch.empty((n, h // bs, w // bs), dtype=torch.float32, device=x.device)
     lib = _lib.load()
     with torch.cuda.device(x.device):
         _lib.check(lib.tmf_sigma0_rgb8(x.data_ptr(), out.data_ptr(), n, h, w, h * w * 3, int(block_size),
@@ -306,10 +311,14 @@ def resize_watermark(watermark, target_height, target_width, preserve_ratio=Fals
 # ---------------------------------------------------------------------------
 # the two entry points the pages call
 # ---------------------------------------------------------------------------
-def _require_block8(block_size):
-    if block_size != 8:
-        raise ValueError(f"block_size {block_size} is not supported: this build implements the reference's "
-                         "BLOCK_SIZE = 8 only (there is no CPU fallback)")
+SUPPORTED_BLOCK_SIZES = (4, 6, 8, 10, 12, 14, 16)   # the UI's slider, embed_watermark_page.py:324-331
+
+
+def _require_supported_block(block_size):
+    if block_size not in SUPPORTED_BLOCK_SIZES:
+        raise ValueError(f"block_size {block_size} is not supported: this build implements the even sizes 4..16 "
+                         "the reference's UI offers (there is no CPU fallback)")
+    return int(block_size)
 
 
 def embed_watermark(image, watermark_data, preserve_ratio=False, custom_settings=None):
@@ -319,7 +328,7 @@ def embed_watermark(image, watermark_data, preserve_ratio=False, custom_settings
     as ``embed_watermark(img, watermark_data, preserve_ratio=True)``."""
     torch = _torch()
     block_size, alpha, mode = _resolve(custom_settings)
-    _require_block8(block_size)
+    _require_supported_block(block_size)
     image = image.convert("RGB")
     wm_img = Image.open(io.BytesIO(watermark_data)) if isinstance(watermark_data, bytes) else watermark_data
     rgb = np.asarray(image)
@@ -336,7 +345,7 @@ def extract_watermark(watermarked_image, original_image, custom_settings=None):
     Called by ``internal_pages/extract_watermark_page.py:293-296``."""
     torch = _torch()
     block_size, alpha, mode = _resolve(custom_settings)
-    _require_block8(block_size)
+    _require_supported_block(block_size)
     a = np.ascontiguousarray(np.asarray(watermarked_image.convert("RGB")))
     b = np.ascontiguousarray(np.asarray(original_image.convert("RGB")))
     if a.shape != b.shape:

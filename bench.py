@@ -235,7 +235,9 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "MP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / len(times), 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "1080p RGB embed, 8x8 DCT+SVD, alpha 0.1 (CPU sample of the batch workload)",
+        "config": {"workload": f"{args.images} x 1080p RGB images per GPU, embed, shared 135x240 map, block 8, alpha 0.1",
+                   "mode": "reference algorithm on the host CPU", "image": "1920x1080x3 u8",
+                   "mix": "50% natural-like, 25% uniform random, 25% flat/black/saturated regions",
                    "sample": sample},
         "cpu_baseline": {"value": round(value, 4), "unit": "MP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 4), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

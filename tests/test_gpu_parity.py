@@ -460,3 +460,16 @@ def test_other_block_sizes_vs_oracle(bs):
     got = W.embed_watermark_batch(imgs, wms, 0.1, bs)
     for k in range(3):
         assert np.abs(got[k].astype(int) - O.embed_array(imgs[k], wms[k], 0.1, bs).astype(int)).max() <= 1
+
+
+def test_watermark_map_is_cached_per_device(golden):
+    g = golden("pil_png_preserve1")
+    png = g["png"].tobytes()
+    W.clear_watermark_cache()
+    img = Image.fromarray(g["rgb"])
+    first = np.array(W.embed_watermark(img, png, True))
+    m1 = W.watermark_map(png, 16, 25, True, device="cuda:0")
+    second = np.array(W.embed_watermark(img, png, True))
+    assert W.watermark_map(png, 16, 25, True, device="cuda:0") is m1 and m1.is_cuda
+    assert np.array_equal(first, second)
+    assert_pixels(first, g["ref_out"], what="cached map")

@@ -132,3 +132,21 @@ def test_shard_ranges_partition_by_image():
             assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
             sizes = [e - s for s, e in r]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_watermark_map_cache_and_decoding_helper(golden):
+    g = golden("pil_png_preserve1")
+    png = g["png"].tobytes()
+    W.clear_watermark_cache()
+    a = W.watermark_map(png, 16, 25, True)
+    assert np.array_equal(a, g["wm"])
+    assert W.watermark_map(png, 16, 25, True) is a                     # second call: cached object
+    assert W.watermark_map(bytearray(png), 16, 25, True) is a
+    b = W.watermark_map(png, 16, 25, False)                            # different key
+    assert b is not a and np.array_equal(b, np.array(O.resize_watermark(png, 16, 25, False)))
+    pil = Image.open(io.BytesIO(png))
+    c = W.watermark_map(pil, 16, 25, True)                             # PIL input: computed, not cached
+    assert c is not a and np.array_equal(c, a)
+    big = W.prepare_for_decoding(Image.fromarray(a), scale=4, border=16)
+    assert big.mode == "L" and big.size == (25 * 4 + 32, 16 * 4 + 32)
+    assert set(np.unique(np.array(big))) <= {0, 255}

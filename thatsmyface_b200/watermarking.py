@@ -24,9 +24,12 @@ compute entry point raises ``RuntimeError``.
 """
 from __future__ import annotations
 
+import collections
+import hashlib
 import io
 import os
 import sys
+import threading
 from typing import Optional, Sequence
 
 import numpy as np
@@ -39,7 +42,8 @@ __all__ = [
     "get_watermark_settings", "rgb_to_ycbcr", "ycbcr_to_rgb", "apply_dct_to_block",
     "apply_idct_to_block", "resize_watermark", "embed_watermark", "extract_watermark",
     "embed_tensor", "extract_tensor", "sigma0_tensor", "svd8x8", "dct8x8",
-    "embed_watermark_batch", "extract_watermark_batch",
+    "embed_watermark_batch", "extract_watermark_batch", "watermark_map", "clear_watermark_cache",
+    "prepare_for_decoding",
 ]
 
 #: mode used when neither ``custom_settings["mode"]`` nor an explicit argument says otherwise.
@@ -309,6 +313,73 @@ def resize_watermark(watermark, target_height, target_width, preserve_ratio=Fals
 
 
 # ---------------------------------------------------------------------------
+# watermark-map cache
+#
+# The embed page encodes ONE QR code and then calls embed_watermark once per
+# uploaded image with the same PNG bytes (embed_watermark_page.py:471-531); the
+# reference re-decodes and re-resizes that PNG every time (watermarking.py:157-180,
+# ~8 ms).  The resized map only depends on (bytes, H//bs, W//bs, preserve_ratio), so
+# it is computed once with the reference's own PIL path and kept - on the host and,
+# per device, in HBM.  Only `bytes` inputs are cached (PIL images are mutable).
+# ---------------------------------------------------------------------------
+_WM_CACHE: "collections.OrderedDict" = collections.OrderedDict()
+_WM_CACHE_MAX = 32
+_WM_CACHE_LOCK = threading.Lock()
+
+
+def watermark_map(watermark_data, target_height, target_width, preserve_ratio=False, device=None):
+    """uint8 ``(target_height, target_width)`` map of ``resize_watermark`` as a NumPy array,
+    or as a CUDA tensor on ``device`` when given.  Cached for ``bytes`` input."""
+    key = None
+    if isinstance(watermark_data, (bytes, bytearray)):
+        digest = hashlib.blake2b(bytes(watermark_data), digest_size=16).digest()
+        key = (digest, int(target_height), int(target_width), bool(preserve_ratio))
+        with _WM_CACHE_LOCK:
+            entry = _WM_CACHE.get(key)
+            if entry is not None:
+                _WM_CACHE.move_to_end(key)
+    else:
+        entry = None
+    if entry is None:
+        img = Image.open(io.BytesIO(bytes(watermark_data))) if key is not None else watermark_data
+        arr = np.ascontiguousarray(np.asarray(resize_watermark(img, target_height, target_width, preserve_ratio)))
+        entry = {"host": arr}
+        if key is not None:
+            with _WM_CACHE_LOCK:
+                _WM_CACHE[key] = entry
+                while len(_WM_CACHE) > _WM_CACHE_MAX:
+                    _WM_CACHE.popitem(last=False)
+    if device is None:
+        return entry["host"]
+    torch = _torch()
+    dev = torch.device(device)
+    dkey = ("dev", dev.index if dev.index is not None else torch.cuda.current_device())
+    t = entry.get(dkey)
+    if t is None:
+        t = torch.from_numpy(entry["host"]).to(dev)
+        entry[dkey] = t
+    return t
+
+
+def clear_watermark_cache():
+    with _WM_CACHE_LOCK:
+        _WM_CACHE.clear()
+
+
+def prepare_for_decoding(extracted, scale=4, threshold=128, border=16):
+    """SURVEY.md 8(f) rank 4 - optional helper, not in the reference: the extracted
+    ``(H//8, W//8)`` map has ~1-2 pixels per QR module, which QR decoders reject;
+    binarise it, upscale by an integer factor (nearest) and add a white quiet zone.
+    Takes / returns a PIL "L" image (what ``extract_watermark`` returns and
+    ``qrcode_to_text`` consumes, extract_watermark_page.py:356-358)."""
+    a = np.asarray(extracted.convert("L") if isinstance(extracted, Image.Image) else extracted)
+    b = np.where(a >= threshold, 255, 0).astype(np.uint8)
+    b = np.kron(b, np.ones((int(scale), int(scale)), np.uint8))
+    b = np.pad(b, int(border), constant_values=255)
+    return Image.fromarray(b)
+
+
+# ---------------------------------------------------------------------------
 # the two entry points the pages call
 # ---------------------------------------------------------------------------
 SUPPORTED_BLOCK_SIZES = (4, 6, 8, 10, 12, 14, 16)   # the UI's slider, embed_watermark_page.py:324-331
@@ -330,12 +401,10 @@ def embed_watermark(image, watermark_data, preserve_ratio=False, custom_settings
     block_size, alpha, mode = _resolve(custom_settings)
     _require_supported_block(block_size)
     image = image.convert("RGB")
-    wm_img = Image.open(io.BytesIO(watermark_data)) if isinstance(watermark_data, bytes) else watermark_data
     rgb = np.asarray(image)
     h, w = rgb.shape[:2]
-    wm_map = np.asarray(resize_watermark(wm_img, h // block_size, w // block_size, preserve_ratio))
     x = torch.from_numpy(np.ascontiguousarray(rgb)).cuda(non_blocking=True)
-    m = torch.from_numpy(np.ascontiguousarray(wm_map)).cuda(non_blocking=True)
+    m = watermark_map(watermark_data, h // block_size, w // block_size, preserve_ratio, device=x.device)
     out = embed_tensor(x, m, alpha, block_size, mode)
     return Image.fromarray(out.cpu().numpy())
 

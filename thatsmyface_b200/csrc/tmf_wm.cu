@@ -297,9 +297,93 @@ __device__ __forceinline__ void prefetch_block_rows_l2(const uint8_t* __restrict
 // With KEEP, row i's luma is parked in shared memory as two float4 at
 // col[(2i) * kThreads] and col[(2i+1) * kThreads] (thread-private column,
 // conflict-free 128-bit accesses) for pass 2.
+// ---- packed fp32 (sm_100 FFMA2 / FADD2 / FMUL2) --------------------------------------
+// Two adjacent pixels ride in one 64-bit register pair.  Each lane of a packed
+// instruction is an ordinary round-to-nearest fp32 operation, so results are
+// bit-identical to the scalar formulas in tmf_fast.cuh (which the host test harness
+// runs); what changes is the issue cost: measured ~1.4 dispatch cycles per FFMA2 against
+// 2 for two FFMAs (profiles/r01_ubench.txt), and fp32 math is over half of this kernel's
+// issue slots.  Scalars broadcast and immediates come for free (FFMA2 Rd, Ra.F32, ...).
+#ifndef TMF_USE_F32X2
+#define TMF_USE_F32X2 1
+#endif
+__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
+
+// magic floats of bytes B and B + 3 (same channel of two adjacent pixels) -> (k0, k1)
+__device__ __forceinline__ float2 bytes_to_float2(const uint32_t (&w)[6], int B) {
+  return __fadd2_rn(make_float2(byte_to_magic(w, B), byte_to_magic(w, B + 3)), bc2(-8388608.0f));
+}
+
+// luma of the 8 pixels of a row as four pairs; same values as tmf::luma255_fast
+__device__ __forceinline__ void row_luma2(const uint32_t (&w)[6], float2 (&y2)[4]) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int B = 6 * p;                 // byte offset of pixel 2p
+    // fma(c, 2^23 + b, -c 2^23) == RN(c b) exactly: blue needs no separate magic subtraction
+    const float2 tb = __ffma2_rn(bc2(0.114f), make_float2(byte_to_magic(w, B + 2), byte_to_magic(w, B + 5)),
+                                 bc2(-0.114f * 8388608.0f));
+    y2[p] = __ffma2_rn(bc2(0.299f), bytes_to_float2(w, B), __ffma2_rn(bc2(0.587f), bytes_to_float2(w, B + 1), tb));
+  }
+}
+
+// Gram matrix in paired form: gp[i][p] = (G[i][2p], G[i][2p+1]) for the pairs of the
+// upper triangle that start at an even column, gd[i] = G[i][i] for odd i.
+struct GramPairs {
+  float2 gp[8][4];
+  float gd[8];
+};
+
+__device__ __forceinline__ void gram_accumulate_row2(const float2 (&y2)[4], GramPairs& G) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float yi = (i & 1) ? y2[i >> 1].y : y2[i >> 1].x;
+    if (i & 1) G.gd[i] = fmaf(yi, yi, G.gd[i]);
+#pragma unroll
+    for (int p = (i + 1) >> 1; p < 4; ++p) G.gp[i][p] = __ffma2_rn(bc2(yi), y2[p], G.gp[i][p]);
+  }
+}
+
+__device__ __forceinline__ void gram_pairs_to_sym(const GramPairs& G, float (&gm)[36]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i & 1) gm[tmf::sym_idx<8>(i, i)] = G.gd[i];
+#pragma unroll
+    for (int p = (i + 1) >> 1; p < 4; ++p) {
+      gm[tmf::sym_idx<8>(i, 2 * p)] = G.gp[i][p].x;
+      gm[tmf::sym_idx<8>(i, 2 * p + 1)] = G.gp[i][p].y;
+    }
+  }
+}
+
+// pass 1 over the 8 rows of a block: Gram matrix of its luma (rolled loop: small code).
+// With KEEP, row i's luma is parked in shared memory as two float4 at
+// col[(2i) * STRIDE] and col[(2i+1) * STRIDE] (thread-private column,
+// conflict-free 128-bit accesses) for pass 2.
 template <int VEC, bool KEEP, int STRIDE = kThreads>
 __device__ __forceinline__ void gram_of_block(const uint8_t* __restrict__ base, size_t pitch, float (&gm)[36],
                                               float4* __restrict__ col = nullptr) {
+#if TMF_USE_F32X2
+  GramPairs G;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    G.gd[i] = 0.0f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) G.gp[i][p] = make_float2(0.0f, 0.0f);
+  }
+#pragma unroll kRowUnroll
+  for (int i = 0; i < 8; ++i) {
+    uint32_t w[6];
+    float2 y2[4];
+    load_row24<VEC>(base + (size_t)i * pitch, w);
+    row_luma2(w, y2);
+    if (KEEP) {
+      col[(2 * i) * STRIDE] = make_float4(y2[0].x, y2[0].y, y2[1].x, y2[1].y);
+      col[(2 * i + 1) * STRIDE] = make_float4(y2[2].x, y2[2].y, y2[3].x, y2[3].y);
+    }
+    gram_accumulate_row2(y2, G);
+  }
+  gram_pairs_to_sym(G, gm);
+#else
 #pragma unroll
   for (int k = 0; k < 36; ++k) gm[k] = 0.0f;
 #pragma unroll kRowUnroll
@@ -320,6 +404,36 @@ __device__ __forceinline__ void gram_of_block(const uint8_t* __restrict__ base, 
     }
     tmf::gram_accumulate_row(y, gm);
   }
+#endif
+}
+
+// pass 2 for one row, packed: bytes of the row, its luma (4 pairs), w (4 pairs), f, c ->
+// six output words.  Same arithmetic as tmf::embed_row_fast + pack4_sat_u8.
+__device__ __forceinline__ void embed_row_fast2(const uint32_t (&w)[6], const float2 (&y2)[4], const float2 (&w2)[4],
+                                                float f, float c, uint32_t (&o)[6]) {
+  float2 acc = __fmul2_rn(y2[0], w2[0]);
+#pragma unroll
+  for (int p = 1; p < 4; ++p) acc = __ffma2_rn(y2[p], w2[p], acc);
+  // tmf::dot8 accumulates sequentially; the pairwise order differs by rounding only in z,
+  // which is scaled by f ~ 1e-3: far below the quantiser's resolution
+  const float du = fmaf(f, acc.x + acc.y, c);
+  int q[24];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int B = 6 * p;
+    const float2 r2 = bytes_to_float2(w, B), g2 = bytes_to_float2(w, B + 1), b2 = bytes_to_float2(w, B + 2);
+    const float2 d2 = __fmul2_rn(bc2(du), w2[p]);
+    const float2 R = __ffma2_rn(bc2(1.0005f), r2, __ffma2_rn(bc2(-8.57e-4f), g2, __ffma2_rn(bc2(3.57e-4f), b2, d2)));
+    const float2 G = __ffma2_rn(bc2(1.36e-4f), r2, __ffma2_rn(bc2(1.00003f), g2, __ffma2_rn(bc2(-1.66e-4f), b2, d2)));
+    const float2 Bv = __ffma2_rn(bc2(-6.37e-4f), r2, __ffma2_rn(bc2(1.37e-4f), g2, __ffma2_rn(bc2(1.0005f), b2, d2)));
+    const float2 tR = __fadd2_rd(R, bc2(12582912.0f)), tG = __fadd2_rd(G, bc2(12582912.0f)),
+                 tB = __fadd2_rd(Bv, bc2(12582912.0f));
+    q[B] = __float_as_int(tR.x) - 0x4B400000; q[B + 1] = __float_as_int(tG.x) - 0x4B400000;
+    q[B + 2] = __float_as_int(tB.x) - 0x4B400000; q[B + 3] = __float_as_int(tR.y) - 0x4B400000;
+    q[B + 4] = __float_as_int(tG.y) - 0x4B400000; q[B + 5] = __float_as_int(tB.y) - 0x4B400000;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) o[k] = tmf::pack4_sat_u8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
 }
 
 // Fused embed, FAST mode.
@@ -356,18 +470,28 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
   }
   // pass 2: the rows again (L1/L2 hits), rank-1 update, colour out, quantise, store
   uint8_t* dst = out + org;
+#if TMF_USE_F32X2
+  const float2 w2[4] = {make_float2(w[0], w[1]), make_float2(w[2], w[3]), make_float2(w[4], w[5]), make_float2(w[6], w[7])};
+#endif
 #pragma unroll kRowUnroll
   for (int i = 0; i < 8; ++i) {
-    float r[8], gg[8], b[8];
-    int q[24];
     uint32_t o[6];
-    load_row_rgb255<VEC>(src + (size_t)i * g.row_pitch, r, gg, b);
     float4 ya = make_float4(0.f, 0.f, 0.f, 0.f), yb = ya;
     if (mark != 0) { ya = col[(2 * i) * kThreads]; yb = col[(2 * i + 1) * kThreads]; }
+#if TMF_USE_F32X2
+    uint32_t wd[6];
+    load_row24<VEC>(src + (size_t)i * g.row_pitch, wd);
+    const float2 y2[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb.x, yb.y), make_float2(yb.z, yb.w)};
+    embed_row_fast2(wd, y2, w2, f, c, o);
+#else
+    float r[8], gg[8], b[8];
+    int q[24];
+    load_row_rgb255<VEC>(src + (size_t)i * g.row_pitch, r, gg, b);
     const float y[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
     tmf::embed_row_fast(r, gg, b, y, w, f, c, q);
 #pragma unroll
     for (int k = 0; k < 6; ++k) o[k] = tmf::pack4_sat_u8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
+#endif
     store_row24<VEC>(dst + (size_t)i * g.row_pitch, o);
   }
 }

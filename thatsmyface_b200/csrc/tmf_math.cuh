@@ -226,6 +226,9 @@ TMF_HD void idct8x8(float* a) {
 //
 // Returns the number of sweeps that performed at least one rotation.
 // ---------------------------------------------------------------------------
+#ifndef TMF_JACOBI_F32X2
+#define TMF_JACOBI_F32X2 1             // packed-fp32 rounds on the device (0: scalar rounds)
+#endif
 #define TMF_JACOBI_TOL 1.0e-6f
 #define TMF_JACOBI_FLOOR 1.0e-14f      // (eps * ||A||_F)^2 with ||A||_F ~ 1
 #define TMF_JACOBI_MAX_SWEEPS 12
@@ -319,6 +322,54 @@ TMF_HD float jacobi_round(float* a, float* v) {
   return worst;
 }
 
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------
+// Packed-fp32 (sm_100 FFMA2/FMUL2) form of the round, device only.  Rows are
+// paired - element (rp, j) holds rows 2rp and 2rp+1 of column j in one 64-bit
+// register pair - which a column rotation / column permutation never separates,
+// and (c, s) enter as broadcast scalars, so a rotation of a column pair costs 4
+// packed instructions per row pair instead of 8 scalar ones per two rows.  Every
+// lane is the same round-to-nearest operation as in the scalar code; only the
+// summation order of the three dot products differs.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float2 tmf_bc2(float x) { return make_float2(x, x); }
+
+__device__ __forceinline__ void rr_apply_rows2(float2* m2, const float* c, const float* s) {
+#pragma unroll
+  for (int rp = 0; rp < 4; ++rp) {
+    float2 t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = m2[8 * rp + j];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 x = t[2 * k], y = t[2 * k + 1];
+      m2[8 * rp + TMF_PI(2 * k)] = __ffma2_rn(tmf_bc2(c[k]), x, __fmul2_rn(tmf_bc2(-s[k]), y));
+      m2[8 * rp + TMF_PI(2 * k + 1)] = __ffma2_rn(tmf_bc2(s[k]), x, __fmul2_rn(tmf_bc2(c[k]), y));
+    }
+  }
+}
+
+template <bool WITH_V>
+__device__ __forceinline__ float jacobi_round2(float2* a2, float2* v2) {
+  float c[4], s[4], worst = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 al = make_float2(0.f, 0.f), be = al, ga = al;
+#pragma unroll
+    for (int rp = 0; rp < 4; ++rp) {
+      const float2 x = a2[8 * rp + 2 * k], y = a2[8 * rp + 2 * k + 1];
+      al = __ffma2_rn(x, x, al);
+      be = __ffma2_rn(y, y, be);
+      ga = __ffma2_rn(x, y, ga);
+    }
+    worst = fmaxf(worst, jacobi_cs(al.x + al.y, be.x + be.y, ga.x + ga.y, c[k], s[k]));
+  }
+  rr_apply_rows2(a2, c, s);
+  if (WITH_V) rr_apply_rows2(v2, c, s);
+  return worst;
+}
+#endif  // __CUDACC__
+
 // Sweeps stop when the largest cosine met during a sweep is below
 // TMF_JACOBI_DONE: Jacobi converges quadratically, so the sweep that just ran
 // leaves cosines of order DONE^2 - no extra sweep is spent only to find out
@@ -344,6 +395,31 @@ TMF_HD int jacobi_svd8(float* a, float* v, float& unscale) {
   }
   int sweeps = 0;
   bool more = live;
+#if defined(__CUDA_ARCH__) && TMF_JACOBI_F32X2
+  // pack row pairs (register renaming), iterate, unpack
+  float2 a2[32], v2[WITH_V ? 32 : 1];
+#pragma unroll
+  for (int rp = 0; rp < 4; ++rp)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a2[8 * rp + j] = make_float2(a[16 * rp + j], a[16 * rp + 8 + j]);
+      if (WITH_V) v2[8 * rp + j] = make_float2(v[16 * rp + j], v[16 * rp + 8 + j]);
+    }
+  for (int it = 0; it < TMF_JACOBI_MAX_SWEEPS && more; ++it) {
+    float worst = 0.0f;
+#pragma unroll 1
+    for (int r = 0; r < 7; ++r) worst = fmaxf(worst, jacobi_round2<WITH_V>(a2, v2));
+    sweeps += (worst > 0.0f) ? 1 : 0;
+    more = worst > TMF_JACOBI_DONE;
+  }
+#pragma unroll
+  for (int rp = 0; rp < 4; ++rp)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[16 * rp + j] = a2[8 * rp + j].x; a[16 * rp + 8 + j] = a2[8 * rp + j].y;
+      if (WITH_V) { v[16 * rp + j] = v2[8 * rp + j].x; v[16 * rp + 8 + j] = v2[8 * rp + j].y; }
+    }
+#else
   for (int it = 0; it < TMF_JACOBI_MAX_SWEEPS && more; ++it) {
     float worst = 0.0f;
 #if defined(__CUDA_ARCH__)
@@ -353,6 +429,7 @@ TMF_HD int jacobi_svd8(float* a, float* v, float& unscale) {
     sweeps += (worst > 0.0f) ? 1 : 0;
     more = worst > TMF_JACOBI_DONE;
   }
+#endif
   return sweeps;
 }
 

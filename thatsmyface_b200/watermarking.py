@@ -392,6 +392,23 @@ def _require_supported_block(block_size):
     return int(block_size)
 
 
+def _pil_to_rgb_array(image):
+    """PIL image of any mode -> C-contiguous uint8 (H, W, 3) array we own.  The reference
+    always calls ``image.convert("RGB")`` (watermarking.py:154), which copies even when the
+    mode already is RGB; the input is never mutated here, so that copy is skipped."""
+    if image.mode != "RGB":
+        image = image.convert("RGB")
+    return np.array(image, dtype=np.uint8)          # one copy out of PIL's storage, writable
+
+
+def _array_to_pil(arr, mode):
+    """Wrap a uint8 array we own as a PIL image without another copy (PIL copies lazily if
+    the caller ever writes to it)."""
+    arr = np.ascontiguousarray(arr)
+    h, w = arr.shape[:2]
+    return Image.frombuffer(mode, (w, h), arr, "raw", mode, 0, 1)
+
+
 def embed_watermark(image, watermark_data, preserve_ratio=False, custom_settings=None):
     """watermarking.py:135-221.  ``image``: PIL image of any mode;
     ``watermark_data``: PNG bytes or PIL image.  Returns a new PIL "RGB" image of
@@ -400,13 +417,12 @@ def embed_watermark(image, watermark_data, preserve_ratio=False, custom_settings
     torch = _torch()
     block_size, alpha, mode = _resolve(custom_settings)
     _require_supported_block(block_size)
-    image = image.convert("RGB")
-    rgb = np.asarray(image)
+    rgb = _pil_to_rgb_array(image)
     h, w = rgb.shape[:2]
-    x = torch.from_numpy(np.ascontiguousarray(rgb)).cuda(non_blocking=True)
+    x = torch.from_numpy(rgb).cuda(non_blocking=True)
     m = watermark_map(watermark_data, h // block_size, w // block_size, preserve_ratio, device=x.device)
     out = embed_tensor(x, m, alpha, block_size, mode)
-    return Image.fromarray(out.cpu().numpy())
+    return _array_to_pil(out.cpu().numpy(), "RGB")
 
 
 def extract_watermark(watermarked_image, original_image, custom_settings=None):
@@ -415,14 +431,14 @@ def extract_watermark(watermarked_image, original_image, custom_settings=None):
     torch = _torch()
     block_size, alpha, mode = _resolve(custom_settings)
     _require_supported_block(block_size)
-    a = np.ascontiguousarray(np.asarray(watermarked_image.convert("RGB")))
-    b = np.ascontiguousarray(np.asarray(original_image.convert("RGB")))
+    a = _pil_to_rgb_array(watermarked_image)
+    b = _pil_to_rgb_array(original_image)
     if a.shape != b.shape:
         raise ValueError(f"watermarked image {a.shape[1]}x{a.shape[0]} and original image "
                          f"{b.shape[1]}x{b.shape[0]} must have the same size")
     out = extract_tensor(torch.from_numpy(a).cuda(non_blocking=True), torch.from_numpy(b).cuda(non_blocking=True),
                          alpha, block_size, mode)
-    return Image.fromarray(out.cpu().numpy())
+    return _array_to_pil(out.cpu().numpy(), "L")
 
 
 # ---------------------------------------------------------------------------

@@ -416,7 +416,8 @@ def main():
         "cpu_baseline": cpu,
         "e2e": {"value": round(e2e_value, 1), "unit": "MP/s", "h2d_bytes_per_step": stats.get("h2d_bytes"),
                 "d2h_bytes_per_step": stats.get("d2h_bytes"), "images_per_step_per_gpu": ne, "steps": e_steps,
-                "matches_device_path": e2e_ok, "timer": "host wall clock around the public API call, synchronised both sides, max over ranks"},
+                "matches_device_path": e2e_ok, "api": "embed_watermark_batch -> tmf_ctx_embed_host_async + tmf_ctx_synchronize (C ABI, host buffers)",
+                "timer": "host wall clock around the public API call, synchronised both sides, max over ranks"},
         "gpu_launches": args.steps * world,
         "clocks": clocks,
         "extract": {"value": round(extract_value, 1), "unit": "MP/s", "ms_per_step": round(x_ms / x_steps, 4),

@@ -101,6 +101,36 @@ int tmf_dct8x8_f32(const float* in, float* out, int64_t nblocks, int inverse, vo
 int tmf_rgb8_to_ycbcr_f32(const uint8_t* rgb, float* ycc, int64_t npixels, void* stream);
 int tmf_ycbcr_f32_to_rgb8(const float* ycc, uint8_t* rgb, int64_t npixels, void* stream);
 
+/* ---- host-buffer pipeline -------------------------------------------------------------
+ * The per-image loop of the embed page (embed_watermark_page.py:492-558) as one call on
+ * HOST memory.  A context owns 3 streams and `depth` device slots on one device; the
+ * batch is cut into chunks of ~chunk_bytes (0 = 96 MiB) and H2D copy, fused kernel and D2H
+ * copy of successive chunks overlap.  Calls enqueue and return; results are in the host
+ * buffers after tmf_ctx_synchronize().  For several GPUs: one context per device, split the
+ * batch by image, enqueue on all, synchronise each (no collective).  A context is not
+ * thread-safe; different contexts are independent.  Host buffers must stay valid until the
+ * synchronise; page-lock them (tmf_pin_host, or any pinned allocator) for real overlap. */
+#define TMF_CTX_MAX_DEPTH 8
+typedef struct tmf_ctx tmf_ctx;
+
+int tmf_ctx_create(tmf_ctx** ctx, int device, size_t chunk_bytes, int depth);
+int tmf_ctx_destroy(tmf_ctx* ctx);
+
+/* images: n x h x w x 3 bytes, tightly packed; wm: (h/B) x (w/B) bytes, one shared map
+ * (wm_shared != 0) or n maps. */
+int tmf_ctx_embed_host_async(tmf_ctx* ctx, const uint8_t* rgb, uint8_t* out, int n, int h, int w,
+                             const uint8_t* wm, int wm_shared, double alpha, int block, int mode);
+/* out_wm: n x (h/B) x (w/B) bytes. */
+int tmf_ctx_extract_host_async(tmf_ctx* ctx, const uint8_t* wmk_rgb, const uint8_t* orig_rgb, uint8_t* out_wm,
+                               int n, int h, int w, double alpha, int block, int mode);
+int tmf_ctx_synchronize(tmf_ctx* ctx);
+/* kernel launches and bytes copied since creation / the last reset (any pointer may be NULL) */
+int tmf_ctx_stats(tmf_ctx* ctx, long long* launches, long long* h2d_bytes, long long* d2h_bytes, int reset);
+
+/* cudaHostRegister / cudaHostUnregister for callers without a CUDA toolchain */
+int tmf_pin_host(void* p, size_t bytes);
+int tmf_unpin_host(void* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,14 +20,11 @@ host_out = torch.empty_like(host_in).pin_memory()
 wm = bench.make_wm_map()
 for depth in (2, 3, 4):
     for mb in (16, 32, 64, 96, 192):
-        orig = pipeline.HostPipeline.__init__.__defaults__
-        pipeline.HostPipeline.__init__.__defaults__ = (depth,) + orig[1:]
-        pipeline.run_batch("embed", host_in, None, wm, 0.1, 8, 1, [0], host_out, chunk_bytes=mb << 20)
+        pipeline.run_batch("embed", host_in, None, wm, 0.1, 8, 1, [0], host_out, chunk_bytes=mb << 20, depth=depth)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(3):
-            pipeline.run_batch("embed", host_in, None, wm, 0.1, 8, 1, [0], host_out, chunk_bytes=mb << 20)
+            pipeline.run_batch("embed", host_in, None, wm, 0.1, 8, 1, [0], host_out, chunk_bytes=mb << 20, depth=depth)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / 3
-        pipeline.HostPipeline.__init__.__defaults__ = orig
         print(f"depth {depth} chunk {mb:4d} MB: {n * bench.PX / dt / 1e6:9.0f} MP/s  ({2 * n * bench.PX * 3 / dt / 1e9:.1f} GB/s PCIe both ways)", flush=True)

@@ -379,7 +379,7 @@ def test_host_pipeline_matches_device_path():
     stats = {}
     piped = run_batch("embed", imgs, None, wm, chunk_bytes=3 * 72 * 96 * 3, stats=stats)
     assert isinstance(piped, np.ndarray) and np.array_equal(piped, direct)
-    assert stats["launches"] == 3 and stats["h2d_bytes"] == imgs.size and stats["d2h_bytes"] == imgs.size
+    assert stats["launches"] == 3 and stats["h2d_bytes"] == imgs.size + wm.size and stats["d2h_bytes"] == imgs.size
     pinned = torch.from_numpy(imgs).pin_memory()
     piped_t = W.embed_watermark_batch(pinned, wm)
     assert isinstance(piped_t, torch.Tensor) and piped_t.is_pinned() and np.array_equal(piped_t.numpy(), direct)
@@ -473,3 +473,45 @@ def test_watermark_map_is_cached_per_device(golden):
     assert W.watermark_map(png, 16, 25, True, device="cuda:0") is m1 and m1.is_cuda
     assert np.array_equal(first, second)
     assert_pixels(first, g["ref_out"], what="cached map")
+
+
+def test_c_abi_host_context_directly():
+    """The host-buffer entry points through ctypes only (no torch on the data path):
+    tmf_pin_host + tmf_ctx_embed_host_async / extract + synchronize + stats."""
+    import ctypes as C
+    from thatsmyface_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(31)
+    imgs = np.ascontiguousarray(np.stack([natural_like(64, 88, s) for s in range(5)]))
+    wms = rng.integers(0, 256, (5, 8, 11), dtype=np.uint8)
+    out = np.empty_like(imgs)
+    ext = np.empty((5, 8, 11), np.uint8)
+    for arr in (imgs, out):
+        _lib.check(lib.tmf_pin_host(arr.ctypes.data, arr.nbytes))
+    h = C.c_void_p()
+    _lib.check(lib.tmf_ctx_create(C.byref(h), 0, 2 * 64 * 88 * 3, 3))
+    try:
+        _lib.check(lib.tmf_ctx_embed_host_async(h, imgs.ctypes.data, out.ctypes.data, 5, 64, 88, wms.ctypes.data, 0,
+                                                0.1, 8, 1))
+        _lib.check(lib.tmf_ctx_synchronize(h))
+        want = W.embed_tensor(torch.from_numpy(imgs).cuda(), torch.from_numpy(wms).cuda(), 0.1, 8, 1).cpu().numpy()
+        assert np.array_equal(out, want)
+        _lib.check(lib.tmf_ctx_extract_host_async(h, out.ctypes.data, imgs.ctypes.data, ext.ctypes.data, 5, 64, 88,
+                                                  0.1, 8, 1))
+        _lib.check(lib.tmf_ctx_synchronize(h))
+        assert np.array_equal(ext, W.extract_tensor(torch.from_numpy(out).cuda(), torch.from_numpy(imgs).cuda(),
+                                                    0.1, 8, 1).cpu().numpy())
+        a, b, c = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        _lib.check(lib.tmf_ctx_stats(h, C.byref(a), C.byref(b), C.byref(c), 1))
+        assert a.value == 6 and b.value == imgs.nbytes * 3 + wms.nbytes and c.value == out.nbytes + ext.nbytes
+        # shared map, second call on the same context, bad block size surfaces as an error code
+        _lib.check(lib.tmf_ctx_embed_host_async(h, imgs.ctypes.data, out.ctypes.data, 5, 64, 88, wms[0].ctypes.data, 1,
+                                                0.1, 8, 0))
+        _lib.check(lib.tmf_ctx_synchronize(h))
+        assert_pixels(out[2], O.embed_array(imgs[2], wms[0]), what="ctx shared map, faithful")
+        assert lib.tmf_ctx_embed_host_async(h, imgs.ctypes.data, out.ctypes.data, 5, 64, 88, wms.ctypes.data, 0,
+                                            0.1, 7, 1) == -2
+    finally:
+        lib.tmf_ctx_destroy(h)
+        for arr in (imgs, out):
+            lib.tmf_unpin_host(arr.ctypes.data)

@@ -50,6 +50,15 @@ def test_argument_validation_happens_before_any_cuda_work(lib):
     assert lib.tmf_svd8x8_f32(None, -1, None, None, None, None, 0, None) == -1
     assert lib.tmf_svd8x8_f32(None, 0, None, None, None, None, 0, None) == 0
     assert lib.tmf_embed_rgb8(None, None, 0, 16, 16, 768, None, 1, 0.1, 8, 0, None) == 0   # empty batch
+    import ctypes as C
+    h = C.c_void_p()
+    assert lib.tmf_ctx_create(C.byref(h), 0, 0, 99) == -1 and "depth" in _lib.last_error()
+    assert lib.tmf_ctx_create(None, 0, 0, 2) == -1
+    if NO_GPU:
+        assert lib.tmf_ctx_create(C.byref(h), 0, 0, 2) == -3 and not h      # no device: CUDA error, no context
+    assert lib.tmf_ctx_embed_host_async(None, None, None, 1, 16, 16, None, 1, 0.1, 8, 1) == -1
+    assert lib.tmf_ctx_synchronize(None) == -1 and lib.tmf_ctx_destroy(None) == 0
+    assert lib.tmf_pin_host(None, 0) == -1
     with pytest.raises(ValueError):
         _lib.check(-1)
     with pytest.raises(RuntimeError):

@@ -24,6 +24,14 @@ PROTOTYPES = {
     "tmf_dct8x8_f32": (_i, [_vp, _vp, _i64, _i, _vp]),
     "tmf_rgb8_to_ycbcr_f32": (_i, [_vp, _vp, _i64, _vp]),
     "tmf_ycbcr_f32_to_rgb8": (_i, [_vp, _vp, _i64, _vp]),
+    "tmf_ctx_create": (_i, [C.POINTER(_vp), _i, _sz, _i]),
+    "tmf_ctx_destroy": (_i, [_vp]),
+    "tmf_ctx_embed_host_async": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _d, _i, _i]),
+    "tmf_ctx_extract_host_async": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _i, _i]),
+    "tmf_ctx_synchronize": (_i, [_vp]),
+    "tmf_ctx_stats": (_i, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _i]),
+    "tmf_pin_host": (_i, [_vp, _sz]),
+    "tmf_unpin_host": (_i, [_vp]),
 }
 
 ERR_BAD_ARG, ERR_UNSUPPORTED_BLOCK, ERR_CUDA = -1, -2, -3

@@ -2,109 +2,84 @@
 
 The reference's embed page walks the uploaded images one at a time
 (``internal_pages/embed_watermark_page.py:492-558``).  Here a batch of host
-images is cut into chunks and each chunk flows H2D copy -> fused kernel -> D2H
-copy on three CUDA streams with ``depth`` device slots, so PCIe in, compute and
-PCIe out overlap.  With several devices the batch is split purely by image
-(contiguous ranges, one pipeline per device, no collective, no peer traffic) and
-all devices are driven asynchronously from this one host thread.
+images goes through the C ABI's host-buffer context (``tmf_ctx_*`` in
+``include/tmf_wm.h``): the batch is cut into chunks and H2D copy, fused kernel and
+D2H copy of successive chunks overlap on three CUDA streams with ``depth`` device
+slots.  With several devices the batch is split purely by image (contiguous
+ranges, one context per device, no collective, no peer traffic); every context is
+enqueued before any is synchronised, so the devices run concurrently from this
+one host thread.
 
-PyTorch supplies device memory, streams, events and pinned memory only.
+The pipeline itself is native (C++/CUDA runtime inside libtmfwm.so); this module
+only validates shapes, hands over host pointers and keeps one context per
+(thread, device).  PyTorch is used for pinned host memory and nothing else.
 """
 from __future__ import annotations
 
+import ctypes as C
+import threading
 from typing import Optional, Sequence
 
 import numpy as np
 
+from . import _lib
 from .constants import ALPHA, BLOCK_SIZE
 
 DEFAULT_CHUNK_BYTES = 96 << 20
+DEFAULT_DEPTH = 2
 
 
 class HostPipeline:
-    """Chunked, stream-overlapped embed/extract for one device and one image size."""
+    """One ``tmf_ctx`` (streams + device slots) on one device.  Not thread-safe; use one
+    per thread (``context_for`` does that)."""
 
-    def __init__(self, device: int, h: int, w: int, chunk_images: int, kind: str, depth: int = 2,
-                 block_size: int = BLOCK_SIZE):
-        from . import watermarking as wmk
+    def __init__(self, device: int, chunk_bytes: int = DEFAULT_CHUNK_BYTES, depth: int = DEFAULT_DEPTH):
+        self._lib = _lib.load()
+        self.device, self.chunk_bytes, self.depth = int(device), int(chunk_bytes), int(depth)
+        h = C.c_void_p()
+        _lib.check(self._lib.tmf_ctx_create(C.byref(h), self.device, self.chunk_bytes, self.depth))
+        self._h = h
 
-        torch = wmk._torch()
-        if kind not in ("embed", "extract"):
-            raise ValueError("kind must be 'embed' or 'extract'")
-        self.torch, self.kind, self.h, self.w = torch, kind, h, w
-        self.device = torch.device("cuda", device)
-        self.chunk, self.depth = max(1, int(chunk_images)), max(1, int(depth))
-        nbh, nbw = h // block_size, w // block_size
-        with torch.cuda.device(self.device):
-            self.s_in, self.s_run, self.s_out = (torch.cuda.Stream() for _ in range(3))
-            mk = lambda *shape: torch.empty(shape, dtype=torch.uint8, device=self.device)
-            self.buf_a = [mk(self.chunk, h, w, 3) for _ in range(self.depth)]
-            if kind == "embed":
-                self.buf_b = None
-                self.buf_o = [mk(self.chunk, h, w, 3) for _ in range(self.depth)]
-                self.buf_wm = [mk(self.chunk, nbh, nbw) for _ in range(self.depth)]
-            else:
-                self.buf_b = [mk(self.chunk, h, w, 3) for _ in range(self.depth)]
-                self.buf_o = [mk(self.chunk, nbh, nbw) for _ in range(self.depth)]
-            self.ev_in = [torch.cuda.Event() for _ in range(self.depth)]
-            self.ev_run = [torch.cuda.Event() for _ in range(self.depth)]
-            self.ev_free = [torch.cuda.Event() for _ in range(self.depth)]   # slot's input buffers reusable
-            self.ev_out = [torch.cuda.Event() for _ in range(self.depth)]    # slot's output buffer reusable
-        self.launches = 0
-        self._step = 0
-        self.h2d_bytes = 0
-        self.d2h_bytes = 0
+    def embed_async(self, src, dst, n, h, w, wm, wm_shared, alpha, block_size, mode):
+        _lib.check(self._lib.tmf_ctx_embed_host_async(self._h, src, dst, n, h, w, wm, 1 if wm_shared else 0,
+                                                      float(alpha), int(block_size), int(mode)))
 
-    def submit(self, src_a, src_b, dst, wm, alpha, block_size, mode):
-        """Queue one chunk (<= self.chunk images).  ``src_*``/``dst`` are CPU uint8
-        tensors (pinned for true asynchrony).  ``wm`` (embed only) is either a
-        device-resident shared map ``(nbh, nbw)`` or a CPU tensor of per-image maps
-        ``(k, nbh, nbw)``, which then rides the H2D stream with the images.
-        Returns immediately."""
-        from . import watermarking as wmk
-
-        torch = self.torch
-        k = src_a.shape[0]
-        slot = self._step % self.depth
-        first_use = self._step < self.depth
-        self._step += 1
-        with torch.cuda.device(self.device):
-            a = self.buf_a[slot][:k]
-            o = self.buf_o[slot][:k]
-            with torch.cuda.stream(self.s_in):
-                if not first_use:
-                    self.s_in.wait_event(self.ev_free[slot])
-                a.copy_(src_a, non_blocking=True)
-                self.h2d_bytes += src_a.numel()
-                if self.kind == "extract":
-                    b = self.buf_b[slot][:k]
-                    b.copy_(src_b, non_blocking=True)
-                    self.h2d_bytes += src_b.numel()
-                wm_dev = wm
-                if self.kind == "embed" and not wm.is_cuda:
-                    wm_dev = self.buf_wm[slot][:k]
-                    wm_dev.copy_(wm, non_blocking=True)
-                    self.h2d_bytes += wm.numel()
-                self.ev_in[slot].record(self.s_in)
-            with torch.cuda.stream(self.s_run):
-                self.s_run.wait_event(self.ev_in[slot])
-                if not first_use:
-                    self.s_run.wait_event(self.ev_out[slot])
-                if self.kind == "embed":
-                    wmk.embed_tensor(a, wm_dev, alpha, block_size, mode, out=o)
-                else:
-                    wmk.extract_tensor(a, self.buf_b[slot][:k], alpha, block_size, mode, out=o)
-                self.launches += 1
-                self.ev_run[slot].record(self.s_run)
-                self.ev_free[slot].record(self.s_run)
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(self.ev_run[slot])
-                dst.copy_(o, non_blocking=True)
-                self.d2h_bytes += o.numel()
-                self.ev_out[slot].record(self.s_out)
+    def extract_async(self, src_a, src_b, dst, n, h, w, alpha, block_size, mode):
+        _lib.check(self._lib.tmf_ctx_extract_host_async(self._h, src_a, src_b, dst, n, h, w, float(alpha),
+                                                        int(block_size), int(mode)))
 
     def synchronize(self):
-        self.s_out.synchronize()
+        _lib.check(self._lib.tmf_ctx_synchronize(self._h))
+
+    def stats(self, reset=False):
+        a, b, c = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        _lib.check(self._lib.tmf_ctx_stats(self._h, C.byref(a), C.byref(b), C.byref(c), 1 if reset else 0))
+        return {"launches": a.value, "h2d_bytes": b.value, "d2h_bytes": c.value}
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.tmf_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # best effort; contexts normally live as long as the thread
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_tls = threading.local()
+
+
+def context_for(device: int, chunk_bytes: int = DEFAULT_CHUNK_BYTES, depth: int = DEFAULT_DEPTH) -> HostPipeline:
+    """The calling thread's context for ``device`` (created on first use)."""
+    cache = getattr(_tls, "ctx", None)
+    if cache is None:
+        cache = _tls.ctx = {}
+    key = (int(device), int(chunk_bytes), int(depth))
+    if key not in cache:
+        cache[key] = HostPipeline(*key)
+    return cache[key]
 
 
 def _as_cpu_u8(x, name):
@@ -126,11 +101,15 @@ def shard_ranges(n: int, parts: int):
 
 def run_batch(kind, a, b, wm_map, alpha=ALPHA, block_size=BLOCK_SIZE, mode=None,
               devices: Optional[Sequence[int]] = None, out=None, chunk_bytes: int = DEFAULT_CHUNK_BYTES,
-              stats: Optional[dict] = None):
+              stats: Optional[dict] = None, depth: int = DEFAULT_DEPTH):
+    """Batched embed / extract on HOST arrays (NumPy or CPU torch, pinned for full overlap)."""
     from . import watermarking as wmk
 
     torch = wmk._torch()
+    if kind not in ("embed", "extract"):
+        raise ValueError("kind must be 'embed' or 'extract'")
     block_size = wmk._require_supported_block(block_size)
+    mode = wmk.DEFAULT_MODE if mode is None else int(mode)
     ta, flavour = _as_cpu_u8(a, "images")
     if ta.dim() != 4 or ta.shape[-1] != 3:
         raise ValueError(f"images must have shape (N, H, W, 3), got {tuple(ta.shape)}")
@@ -145,13 +124,17 @@ def run_batch(kind, a, b, wm_map, alpha=ALPHA, block_size=BLOCK_SIZE, mode=None,
     if not devices:
         raise ValueError("devices must not be empty")
 
+    tw, shared = None, True
     if kind == "embed":
         tw, _ = _as_cpu_u8(wm_map, "watermark_map")
-        if tuple(tw.shape) not in ((nbh, nbw), (n, nbh, nbw)):
+        if tuple(tw.shape) == (nbh, nbw):
+            shared = True
+        elif tuple(tw.shape) == (n, nbh, nbw):
+            shared = False
+        else:
             raise ValueError(f"watermark map must be {(nbh, nbw)} or {(n, nbh, nbw)}, got {tuple(tw.shape)}")
         out_shape = (n, h, w, 3)
     else:
-        tw = None
         out_shape = (n, nbh, nbw)
     if out is None:
         tout = torch.empty(out_shape, dtype=torch.uint8, pin_memory=ta.is_pinned())
@@ -160,35 +143,31 @@ def run_batch(kind, a, b, wm_map, alpha=ALPHA, block_size=BLOCK_SIZE, mode=None,
         if tuple(tout.shape) != out_shape:
             raise ValueError(f"out must have shape {out_shape}")
 
-    img_bytes = max(1, h * w * 3)
-    chunk = max(1, min(chunk_bytes // img_bytes, max(1, -(-n // len(devices)))))
-    pipes, wms, work = [], [], []
+    img_bytes, out_bytes, map_bytes = h * w * 3, int(np.prod(out_shape[1:])), nbh * nbw
+    ctxs = []
     for dev, (lo, hi) in zip(devices, shard_ranges(n, len(devices))):
         if hi <= lo:
             continue
-        p = HostPipeline(dev, h, w, min(chunk, hi - lo), kind, block_size=block_size)
-        pipes.append(p)
-        if kind == "embed" and tw.dim() == 2:
-            wms.append(tw.to(p.device))          # shared map: resident before the first launch
-            torch.cuda.current_stream(p.device).synchronize()
+        ctx = context_for(dev, chunk_bytes, depth)
+        if stats is not None:
+            ctx.stats(reset=True)
+        src = ta.data_ptr() + lo * img_bytes
+        dst = tout.data_ptr() + lo * out_bytes
+        if kind == "embed":
+            wm_ptr = tw.data_ptr() + (0 if shared else lo * map_bytes)
+            ctx.embed_async(src, dst, hi - lo, h, w, wm_ptr, shared, alpha, block_size, mode)
         else:
-            wms.append(None)
-        work.append([(s, min(s + p.chunk, hi)) for s in range(lo, hi, p.chunk)])
-    # round-robin over devices so that every device has work queued early
-    for step in range(max((len(wk) for wk in work), default=0)):
-        for p, wm_dev, wk in zip(pipes, wms, work):
-            if step >= len(wk):
-                continue
-            s, e = wk[step]
-            wm_chunk = tw[s:e] if (kind == "embed" and wm_dev is None) else wm_dev
-            p.submit(ta[s:e], tb[s:e] if tb is not None else None, tout[s:e], wm_chunk, alpha, block_size, mode)
-    for p in pipes:
-        p.synchronize()
+            ctx.extract_async(src, tb.data_ptr() + lo * img_bytes, dst, hi - lo, h, w, alpha, block_size, mode)
+        ctxs.append(ctx)
+    for ctx in ctxs:       # every device has its work queued before the first wait
+        ctx.synchronize()
     if stats is not None:
-        stats["launches"] = sum(p.launches for p in pipes)
-        stats["h2d_bytes"] = sum(p.h2d_bytes for p in pipes)
-        stats["d2h_bytes"] = sum(p.d2h_bytes for p in pipes)
-        stats["chunk_images"] = chunk
+        tot = {"launches": 0, "h2d_bytes": 0, "d2h_bytes": 0}
+        for ctx in ctxs:
+            for k, v in ctx.stats().items():
+                tot[k] += v
+        stats.update(tot)
+        stats["chunk_images"] = max(1, min(chunk_bytes // max(1, img_bytes), max(1, -(-n // len(devices)))))
     if out is not None:
         return out
     return tout.numpy() if flavour == "numpy" else tout

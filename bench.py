@@ -142,7 +142,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"],
+                                          "-i", str(self.index), "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -155,9 +155,9 @@ class ClockSampler:
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for (_, l) in self.lines]
+        rows = [l for (t, l) in self.lines if t0 - 0.02 <= t <= t1 + 0.04] or [l for (_, l) in self.lines]
         sm, mx, reasons = [], [], set()
         for l in rows:
             f = [x.strip() for x in l.split(",")]

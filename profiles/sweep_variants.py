@@ -14,8 +14,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
-VARIANTS = {f"u{u}_c{c}_t{t}": {"TMF_ROW_UNROLL": u, "TMF_FAST_MIN_CTAS": c, "TMF_EMBED_THREADS": t}
-            for u, c, t in itertools.product((1, 2), (4, 6), (128, 256, 384))}
+VARIANTS = {f"u{u}_c{c}": {"TMF_ROW_UNROLL": u, "TMF_FAST_MIN_CTAS": c}
+            for u, c in itertools.product((4, 8), (4, 5, 6, 7))}
 
 
 def build():

@@ -38,13 +38,16 @@ constexpr int kThreads = 128;
 
 // tunables of the fast kernels (profiles/sweep_variants.py builds and times the alternatives)
 #ifndef TMF_ROW_UNROLL
-#define TMF_ROW_UNROLL 1      // rows per iteration of the rolled row loops (1, 2, 4)
+#define TMF_ROW_UNROLL 4      // rows per iteration of the rolled row loops (1, 2, 4, 8)
 #endif
 #ifndef TMF_L2_LOOKAHEAD
 #define TMF_L2_LOOKAHEAD 0    // blocks ahead whose rows are prefetched into L2 (0 = off)
 #endif
 #ifndef TMF_FAST_MIN_CTAS
-#define TMF_FAST_MIN_CTAS 6   // __launch_bounds__ minimum CTAs/SM of the fast kernels
+#define TMF_FAST_MIN_CTAS 6   // __launch_bounds__ minimum CTAs/SM of the fast extract / sigma0 kernels
+#endif
+#ifndef TMF_EMBED_MIN_CTAS
+#define TMF_EMBED_MIN_CTAS 5  // ... of the fast embed kernel (best of profiles/r01_sweep_variants.txt, table 4)
 #endif
 constexpr int kRowUnroll = TMF_ROW_UNROLL;
 
@@ -446,7 +449,7 @@ __device__ __forceinline__ void embed_row_fast2(const uint32_t (&w)[6], const fl
 // 24-byte row pieces cost more L1 wavefronts than the skipped work saves
 // (profiles/r01_sweep_variants.txt, third table).
 template <int VEC>
-__global__ void __launch_bounds__(kThreads, TMF_FAST_MIN_CTAS)
+__global__ void __launch_bounds__(kThreads, TMF_EMBED_MIN_CTAS)
 k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGeom g,
              const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
   const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;

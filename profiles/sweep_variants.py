@@ -14,8 +14,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
-VARIANTS = {f"u{u}_c{c}": {"TMF_ROW_UNROLL": u, "TMF_FAST_MIN_CTAS": c}
-            for u, c in itertools.product((4, 8), (4, 5, 6, 7))}
+VARIANTS = {f"qimad{i}": {"TMF_QUANT_IMAD": i} for i in (0, 1)}
 
 
 def build():

@@ -47,7 +47,7 @@ constexpr int kThreads = 128;
 #define TMF_FAST_MIN_CTAS 6   // __launch_bounds__ minimum CTAs/SM of the fast extract / sigma0 kernels
 #endif
 #ifndef TMF_EMBED_MIN_CTAS
-#define TMF_EMBED_MIN_CTAS 5  // ... of the fast embed kernel (best of profiles/r01_sweep_variants.txt, table 4)
+#define TMF_EMBED_MIN_CTAS 6  // ... of the fast embed kernel (profiles/r01_sweep_variants.txt, tables 4-5)
 #endif
 constexpr int kRowUnroll = TMF_ROW_UNROLL;
 
@@ -264,12 +264,26 @@ k_sigma0_faithful(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, B
 // ---------------------------------------------------------------------------
 // byte B of the 24-byte row as a float, via the 2^23 magic number (PRMT + FADD,
 // both full-rate pipes; the I2F.U8 conversion pipe is much narrower)
-// byte B of the row as the "magic" float 2^23 + k (one half-rate PRMT or SHF; the
-// bit pattern 0x4B0000kk is exactly 8388608 + k)
+// byte B of the row as the "magic" float 2^23 + k (the bit pattern 0x4B0000kk is exactly
+// 8388608 + k).  Bytes 0-2 take one PRMT (ALU pipe, half rate); byte 3 takes one
+// IMAD.HI - hi32(x * 256) + 0x4B000000 = (x >> 24) + magic - which runs on the FMA pipe:
+// ncu shows the ALU pipe as the busier one (52 % vs 36 %, math_pipe_throttle stalls), so a
+// quarter of the extractions is moved across.
+#ifndef TMF_BYTE3_IMAD
+#define TMF_BYTE3_IMAD 1
+#endif
 __device__ __forceinline__ float byte_to_magic(const uint32_t (&w)[6], int B) {
   const uint32_t x = w[B >> 2];
-  const uint32_t m = ((B & 3) == 3) ? __funnelshift_r(x, 0x004B0000u, 24)        // (x >> 24) | 0x4B000000
-                                    : __byte_perm(x, 0x4B000000u, 0x7650u | (uint32_t)(B & 3));
+  uint32_t m;
+  if ((B & 3) == 3) {
+#if TMF_BYTE3_IMAD
+    asm("mad.hi.u32 %0, %1, 256, 0x4B000000;" : "=r"(m) : "r"(x));
+#else
+    m = __funnelshift_r(x, 0x004B0000u, 24);        // (x >> 24) | 0x4B000000
+#endif
+  } else {
+    m = __byte_perm(x, 0x4B000000u, 0x7650u | (uint32_t)(B & 3));
+  }
   return __uint_as_float(m);
 }
 __device__ __forceinline__ float byte_to_float(const uint32_t (&w)[6], int B) {
@@ -410,6 +424,24 @@ __device__ __forceinline__ void gram_of_block(const uint8_t* __restrict__ base, 
 #endif
 }
 
+// bits(floor-biased float) - 0x4B400000 = the integer level.  TMF_QUANT_IMAD picks the
+// pipe: 0 = IADD3 (ALU pipe), 1 = IMAD x*1+c (FMA pipe), 2 = alternate.
+#ifndef TMF_QUANT_IMAD
+#define TMF_QUANT_IMAD 0
+#endif
+__device__ __forceinline__ int unbias_imad(float t) {
+  int r;
+  asm("mad.lo.s32 %0, %1, 1, %2;" : "=r"(r) : "r"(__float_as_int(t)), "r"(-0x4B400000));
+  return r;
+}
+__device__ __forceinline__ int unbias(float t) {
+#if TMF_QUANT_IMAD == 1
+  return unbias_imad(t);
+#else
+  return __float_as_int(t) - 0x4B400000;
+#endif
+}
+
 // pass 2 for one row, packed: bytes of the row, its luma (4 pairs), w (4 pairs), f, c ->
 // six output words.  Same arithmetic as tmf::embed_row_fast + pack4_sat_u8.
 __device__ __forceinline__ void embed_row_fast2(const uint32_t (&w)[6], const float2 (&y2)[4], const float2 (&w2)[4],
@@ -431,9 +463,8 @@ __device__ __forceinline__ void embed_row_fast2(const uint32_t (&w)[6], const fl
     const float2 Bv = __ffma2_rn(bc2(-6.37e-4f), r2, __ffma2_rn(bc2(1.37e-4f), g2, __ffma2_rn(bc2(1.0005f), b2, d2)));
     const float2 tR = __fadd2_rd(R, bc2(12582912.0f)), tG = __fadd2_rd(G, bc2(12582912.0f)),
                  tB = __fadd2_rd(Bv, bc2(12582912.0f));
-    q[B] = __float_as_int(tR.x) - 0x4B400000; q[B + 1] = __float_as_int(tG.x) - 0x4B400000;
-    q[B + 2] = __float_as_int(tB.x) - 0x4B400000; q[B + 3] = __float_as_int(tR.y) - 0x4B400000;
-    q[B + 4] = __float_as_int(tG.y) - 0x4B400000; q[B + 5] = __float_as_int(tB.y) - 0x4B400000;
+    q[B] = unbias(tR.x); q[B + 1] = unbias(tG.x); q[B + 2] = unbias(tB.x);
+    q[B + 3] = unbias(tR.y); q[B + 4] = unbias(tG.y); q[B + 5] = unbias(tB.y);
   }
 #pragma unroll
   for (int k = 0; k < 6; ++k) o[k] = tmf::pack4_sat_u8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);

@@ -394,7 +394,7 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        rows = 128
+        rows = 512        # ~2.5 s of wall time per core at ~0.4 MP/s/core: ~40 core-seconds in all
         v, dt = cpu_baseline_run(cores, rows)
         cpu = {"value": round(v, 4), "unit": "MP/s", "cores": cores, "kind": "port",
                "sample": f"{cores} strips of 1920x{rows} px (one per core) of the same synthetic 1080p images, oracle "

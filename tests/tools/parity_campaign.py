@@ -1,11 +1,11 @@
-"""Randomised parity campaign on the GPU box: many small images of mixed content, both
+"""(Under tests/: the oracle is the checker.)  Randomised parity campaign on the GPU box: many small images of mixed content, both
 modes, several alphas and block sizes, CUDA path (through the C ABI) vs the oracle.
-Prints one JSON summary.  python profiles/parity_campaign.py [images_per_kind]"""
+Prints one JSON summary.  python tests/tools/parity_campaign.py [images_per_kind]"""
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch

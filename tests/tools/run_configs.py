@@ -1,14 +1,15 @@
 """BASELINE.json configs 1, 2, 4 and 5 on one B200, for the record (bench.py is config 3).
-Writes one JSON document; run on the GPU box:  python profiles/run_configs.py > gpurun_out/rNN_configs.json"""
+Lives under tests/ because it uses the oracle as its checker and CPU timing reference.
+Writes one JSON document; run on the GPU box:  python tests/tools/run_configs.py > gpurun_out/rNN_configs.json"""
 import json
 import os
 import statistics
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))   # qr_util
 
 import numpy as np
 import torch

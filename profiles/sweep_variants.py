@@ -14,7 +14,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
-VARIANTS = {f"qimad{i}": {"TMF_QUANT_IMAD": i} for i in (0, 1)}
+VARIANTS = {f"bulk{a}": {"TMF_BULK_AHEAD": a} for a in (0, 148, 888, 1776)}
 
 
 def build():

@@ -515,3 +515,23 @@ def test_c_abi_host_context_directly():
         lib.tmf_ctx_destroy(h)
         for arr in (imgs, out):
             lib.tmf_unpin_host(arr.ctypes.data)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_8k_image_blocks_are_local(mode):
+    """BASELINE config 5's largest image (7680x4320, 518 400 blocks): round trip on the
+    device, and - because every block is independent - a block-aligned crop of the result
+    must equal the oracle's embedding of that crop."""
+    h, w = 4320, 7680
+    g = torch.Generator(device="cuda").manual_seed(5)
+    yy = torch.arange(h, device="cuda").view(h, 1, 1)
+    xx = torch.arange(w, device="cuda").view(1, w, 1)
+    img = (115 + 60 * torch.sin(xx / 131.0) * torch.cos(yy / 89.0) + torch.randn((h, w, 3), device="cuda", generator=g) * 7)
+    img = img.clamp(0, 255).to(torch.uint8)
+    wm = (torch.rand((h // 8, w // 8), device="cuda", generator=g) < 0.5).to(torch.uint8) * 255
+    out = W.embed_tensor(img, wm, mode=mode)
+    assert torch.equal(W.extract_tensor(out, img, mode=mode) >= 128, wm >= 128)
+    y0, x0 = 4056, 7416                                        # bottom-right region, multiples of 8
+    crop = img[y0:y0 + 264, x0:x0 + 264].cpu().numpy()
+    ref = O.embed_array(crop, wm[y0 // 8:y0 // 8 + 33, x0 // 8:x0 // 8 + 33].cpu().numpy())
+    assert_pixels(out[y0:y0 + 264, x0:x0 + 264].cpu().numpy(), ref, what="8K crop")

@@ -310,6 +310,34 @@ __device__ __forceinline__ void prefetch_block_rows_l2(const uint8_t* __restrict
   for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)i * pitch));
 }
 
+// TMA-engine bulk prefetch into L2 (cp.async.bulk.prefetch.L2) of the 8 image rows of the
+// tile that the CTA `ahead` CTAs further on will own: one thread issues at most 16
+// instructions for 24 KB, so - unlike the per-thread look-ahead that lost throughput - it
+// is free in issue slots.  Needs 16-byte aligned segments (even block offsets, 3W % 16 == 0);
+// the caller checks `ok16`.
+#ifndef TMF_BULK_AHEAD
+#define TMF_BULK_AHEAD 0      // CTAs of look-ahead (0 = off)
+#endif
+__device__ __forceinline__ void bulk_prefetch_tile(const uint8_t* __restrict__ base, const BlockGeom& g, long long gb0) {
+  long long first = gb0, left = kThreads;
+  if (first >= g.total_blocks) return;
+  if (first + left > g.total_blocks) left = g.total_blocks - first;
+  while (left > 0) {
+    long long img; int by, bx;
+    const size_t org = block_origin(g, first, img, by, bx);
+    long long run = g.nbw - bx;                       // blocks to the end of this block-row
+    if (run > left) run = left;
+    const unsigned bytes = (unsigned)(run * 24);
+    if ((bytes & 15u) == 0 && ((org & 15) == 0)) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + org + (size_t)r * g.row_pitch), "r"(bytes));
+    }
+    first += run;
+    left -= run;
+  }
+}
+
 // pass 1 over the 8 rows of a block: Gram matrix of its luma (rolled loop: small code).
 // With KEEP, row i's luma is parked in shared memory as two float4 at
 // col[(2i) * kThreads] and col[(2i+1) * kThreads] (thread-private column,
@@ -491,6 +519,8 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
   __shared__ float4 lum[16 * kThreads];      // 32 KB: the block's luma, thread-private column
   float4* col = lum + threadIdx.x;
   prefetch_block_rows(src, g.row_pitch);
+  if (TMF_BULK_AHEAD > 0 && VEC == 8 && threadIdx.x == 0)
+    bulk_prefetch_tile(rgb, g, ((long long)blockIdx.x + TMF_BULK_AHEAD) * kThreads);
   const long long wi = (wm_shared ? 0 : img * g.blocks_per_img) + (long long)by * g.nbw + bx;
   const uint32_t mark = (uint32_t)__ldg(wm + wi);
   float w[8], f = 0.0f, c = 0.0f;
@@ -541,6 +571,10 @@ k_extract_fast(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ orig
   float gm[36];
   prefetch_block_rows(wmk + org, g.row_pitch);
   prefetch_block_rows(orig + org, g.row_pitch);
+  if (TMF_BULK_AHEAD > 0 && VEC == 8 && threadIdx.x == 0) {
+    bulk_prefetch_tile(wmk, g, ((long long)blockIdx.x + TMF_BULK_AHEAD) * kThreads);
+    bulk_prefetch_tile(orig, g, ((long long)blockIdx.x + TMF_BULK_AHEAD) * kThreads);
+  }
   if (TMF_L2_LOOKAHEAD > 0 && gb + TMF_L2_LOOKAHEAD < g.total_blocks) {
     long long img2; int by2, bx2;
     const size_t o2 = block_origin(g, gb + TMF_L2_LOOKAHEAD, img2, by2, bx2);

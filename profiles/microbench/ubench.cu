@@ -113,6 +113,20 @@ BENCH(k_mix_8ffma_4f2ip, MIXDECL, FF8 OP_F2IP(u0, a0) OP_F2IP(u1, a1) OP_F2IP(u2
 BENCH(k_mix_8ffma_2mufu, MIXDECL, FF8 OP_RSQ(a0) OP_RSQ(a1), MIXSINK)
 BENCH(k_mix_8ffma_only, MIXDECL, FF8, MIXSINK)
 
+
+// u8 -> f32 conversion alternatives inside an FMA-heavy loop: per iteration 8 FFMA plus NCONV
+// conversions of byte 1 of a word, each added into a live accumulator.
+#define CONV_DECL float a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7, acc = 0.f; \
+  unsigned u0 = threadIdx.x * 2654435761u, u1 = u0 * 3u, u2 = u0 * 5u, u3 = u0 * 7u; const unsigned kmag = 0x4B000000u | (unsigned)(clk[1] & 1)
+#define CONV_SINK if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 + acc + (float)(u0 ^ u1 ^ u2 ^ u3) == 12345.678f) sink[0] = a0
+#define CV_MAGIC(u) { unsigned m; asm volatile("prmt.b32 %0, %1, %2, 0x7651;" : "=r"(m) : "r"(u), "r"(kmag)); acc += __uint_as_float(m) - 8388608.0f; u += 0x01010101u; }
+#define CV_I2F(u) { float f; asm volatile("{ .reg .b8 x0,x1,x2,x3; mov.b32 {x0,x1,x2,x3}, %1; cvt.rn.f32.u8 %0, x1; }" : "=f"(f) : "r"(u)); acc += f; u += 0x01010101u; }
+BENCH(k_conv_magic_x2, CONV_DECL, FF8 CV_MAGIC(u0) CV_MAGIC(u1), CONV_SINK)
+BENCH(k_conv_i2f_x2, CONV_DECL, FF8 CV_I2F(u0) CV_I2F(u1), CONV_SINK)
+BENCH(k_conv_magic_x4, CONV_DECL, FF8 CV_MAGIC(u0) CV_MAGIC(u1) CV_MAGIC(u2) CV_MAGIC(u3), CONV_SINK)
+BENCH(k_conv_i2f_x4, CONV_DECL, FF8 CV_I2F(u0) CV_I2F(u1) CV_I2F(u2) CV_I2F(u3), CONV_SINK)
+BENCH(k_conv_mixed_3m1i, CONV_DECL, FF8 CV_MAGIC(u0) CV_MAGIC(u1) CV_MAGIC(u2) CV_I2F(u3), CONV_SINK)
+
 struct T { const char* name; void (*k)(long long*, float*); int ops; };
 
 int main() {
@@ -136,6 +150,10 @@ int main() {
     {"mix: 8 ffma + 8 prmt  (per iter = 1 seq)", k_mix_8ffma_8prmt, 1}, {"mix: 8 ffma + 4 prmt", k_mix_8ffma_4prmt, 1},
     {"mix: 8 ffma only", k_mix_8ffma_only, 1}, {"mix: 8 ffma + 2 f2ip.sat.u8", k_mix_8ffma_2f2ip, 1},
     {"mix: 8 ffma + 4 f2ip.sat.u8", k_mix_8ffma_4f2ip, 1}, {"mix: 8 ffma + 2 mufu.rsq", k_mix_8ffma_2mufu, 1},
+    {"conv: 8 ffma + 2 x (prmt+fadd magic, +fadd acc, +iadd)", k_conv_magic_x2, 1},
+    {"conv: 8 ffma + 2 x (i2f.u8 byte1, +fadd acc, +iadd)", k_conv_i2f_x2, 1},
+    {"conv: 8 ffma + 4 x magic", k_conv_magic_x4, 1}, {"conv: 8 ffma + 4 x i2f.u8", k_conv_i2f_x4, 1},
+    {"conv: 8 ffma + 3 x magic + 1 x i2f.u8", k_conv_mixed_3m1i, 1},
     {"mix: 4 ffma2 + 8 prmt (same flops)", k_mix_4ffma2_8prmt, 1}, {"mix: 4 ffma2 + 4 prmt", k_mix_4ffma2_4prmt, 1},
   };
   printf("device SMs=%d clockRate=%d kHz; rows are iterations of the listed sequence per clk per SM (1024 thr/SM)\n", sms, clk_khz);

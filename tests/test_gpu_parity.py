@@ -535,3 +535,48 @@ def test_8k_image_blocks_are_local(mode):
     crop = img[y0:y0 + 264, x0:x0 + 264].cpu().numpy()
     ref = O.embed_array(crop, wm[y0 // 8:y0 // 8 + 33, x0 // 8:x0 // 8 + 33].cpu().numpy())
     assert_pixels(out[y0:y0 + 264, x0:x0 + 264].cpu().numpy(), ref, what="8K crop")
+
+
+def test_concurrent_sessions_and_determinism():
+    """Streamlit runs every session's script on its own thread (SURVEY.md 8(b) threading):
+    the library must be re-entrant.  8 threads embed + extract different images through the
+    PIL API and the batch API at once; results must equal the single-threaded ones, and a
+    repeated call must be bit-identical."""
+    import threading
+    from thatsmyface_b200.pipeline import pinned
+
+    rng = np.random.default_rng(77)
+    jobs = []
+    for k in range(8):
+        rgb = natural_like(120 + 8 * k, 200 - 8 * k, 40 + k)
+        wm = rng.integers(0, 256, (rgb.shape[0] // 8, rgb.shape[1] // 8), dtype=np.uint8)
+        jobs.append((rgb, wm))
+    want = [gpu_embed(rgb, wm, mode=MODE_FAST) for rgb, wm in jobs]
+    assert all(np.array_equal(gpu_embed(rgb, wm, mode=MODE_FAST), w) for (rgb, wm), w in zip(jobs, want))
+    got, errs = [None] * 8, []
+
+    def work(k):
+        try:
+            rgb, wm = jobs[k]
+            for _ in range(5):
+                s = {"block_size": 8, "alpha": 0.1, "mode": MODE_FAST}
+                a = np.array(W.embed_watermark(Image.fromarray(rgb), Image.fromarray(wm), False, s))
+                batch = np.ascontiguousarray(np.stack([rgb, rgb]))
+                out = np.empty_like(batch)
+                with pinned(batch, out):
+                    W.embed_watermark_batch(batch, wm, mode=MODE_FAST, out=out)
+                e = np.array(W.extract_watermark(Image.fromarray(a), Image.fromarray(rgb), s))
+                assert np.array_equal(out[0], a) and np.array_equal(out[1], a)
+                assert e.shape == wm.shape
+            got[k] = a
+        except Exception as ex:   # surfaced below
+            errs.append(repr(ex))
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for k in range(8):
+        assert np.array_equal(got[k], want[k]), k

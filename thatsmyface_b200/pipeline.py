@@ -68,6 +68,35 @@ class HostPipeline:
             pass
 
 
+class pinned:
+    """Context manager that page-locks NumPy arrays for the duration of a batch call, so the
+    pipeline's copies are truly asynchronous (tmf_pin_host / tmf_unpin_host)::
+
+        with pinned(images, out):
+            embed_watermark_batch(images, wm, out=out)
+    """
+
+    def __init__(self, *arrays):
+        self.arrays = [a for a in arrays if a is not None]
+        self._done = []
+
+    def __enter__(self):
+        lib = _lib.load()
+        for a in self.arrays:
+            if not (isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"]):
+                raise ValueError("pinned() takes C-contiguous NumPy arrays")
+            _lib.check(lib.tmf_pin_host(a.ctypes.data, a.nbytes))
+            self._done.append(a)
+        return self
+
+    def __exit__(self, *exc):
+        lib = _lib.load()
+        for a in self._done:
+            lib.tmf_unpin_host(a.ctypes.data)
+        self._done = []
+        return False
+
+
 _tls = threading.local()
 
 

@@ -236,11 +236,14 @@ k_extract_faithful(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ 
   float* col = sm + threadIdx.x;
   prefetch_block_rows(wmk + org, g.row_pitch);
   prefetch_block_rows(orig + org, g.row_pitch);
-  float a[64];
-  load_luma_block<VEC>(wmk + org, g.row_pitch, col, a);
-  const float sw = tmf::sigma0_block_faithful(a, nullptr);
-  load_luma_block<VEC>(orig + org, g.row_pitch, col, a);
-  const float so = tmf::sigma0_block_faithful(a, nullptr);
+  float sw = 0.0f, so = 0.0f;
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {          // one copy of the code for both images
+    float a[64];
+    load_luma_block<VEC>((which == 0 ? wmk : orig) + org, g.row_pitch, col, a);
+    const float sg = tmf::sigma0_block_faithful(a, nullptr);
+    if (which == 0) sw = sg; else so = sg;
+  }
   out_wm[gb] = (uint8_t)tmf::extract_level(sw, so, alpha);
 }
 

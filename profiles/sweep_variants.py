@@ -14,7 +14,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
-VARIANTS = {f"bulk{a}": {"TMF_BULK_AHEAD": a} for a in (0, 148, 888, 1776)}
+VARIANTS = {f"faith_c{c}": {"TMF_FAITHFUL_MIN_CTAS": c} for c in (2, 3)}
 
 
 def build():
@@ -50,8 +50,9 @@ def run_one(images):
     out = torch.empty_like(imgs)
     ext = torch.empty((images, bench.H // 8, bench.W // 8), dtype=torch.uint8, device=dev)
     res = {}
-    for name, fn in (("embed", lambda: W.embed_tensor(imgs, wm, 0.1, 8, 1, out=out)),
-                     ("extract", lambda: W.extract_tensor(out, imgs, 0.1, 8, 1, out=ext))):
+    mode = int(os.environ.get("TMF_SWEEP_MODE", "1"))
+    for name, fn in (("embed", lambda: W.embed_tensor(imgs, wm, 0.1, 8, mode, out=out)),
+                     ("extract", lambda: W.extract_tensor(out, imgs, 0.1, 8, mode, out=ext))):
         for _ in range(3):
             fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -349,20 +349,49 @@ __device__ __forceinline__ void rr_apply_rows2(float2* m2, const float* c, const
   }
 }
 
+// squared norms of the 8 columns (by position), from the packed block
+__device__ __forceinline__ void column_norms2_packed(const float2* a2, float* n2) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int rp = 0; rp < 4; ++rp) acc = __ffma2_rn(a2[8 * rp + j], a2[8 * rp + j], acc);
+    n2[j] = acc.x + acc.y;
+  }
+}
+
+// One round.  The squared column norms are carried along instead of being recomputed for
+// every pair: a rotation by tan t changes them by exactly -/+ t*gamma, so only the cross
+// product gamma needs a pass over the column (4 packed FMAs instead of 12).  The carried
+// values are refreshed from the data at the start of every sweep (jacobi_svd8), which
+// bounds the drift; they only steer the rotation angle and the skip tests, never the
+// result (singular values are taken from the columns at the end).
+// (Used for the values-only solve; with V in registers as well the 8 extra live values
+// cost more in spills than the saved FMAs bring - measured - so that variant recomputes.)
 template <bool WITH_V>
-__device__ __forceinline__ float jacobi_round2(float2* a2, float2* v2) {
-  float c[4], s[4], worst = 0.0f;
+__device__ __forceinline__ float jacobi_round2(float2* a2, float2* v2, float* n2) {
+  float c[4], s[4], nn[8], worst = 0.0f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    float2 al = make_float2(0.f, 0.f), be = al, ga = al;
+    float2 ga = make_float2(0.f, 0.f), al2 = ga, be2 = ga;
 #pragma unroll
     for (int rp = 0; rp < 4; ++rp) {
       const float2 x = a2[8 * rp + 2 * k], y = a2[8 * rp + 2 * k + 1];
-      al = __ffma2_rn(x, x, al);
-      be = __ffma2_rn(y, y, be);
       ga = __ffma2_rn(x, y, ga);
+      if (WITH_V) { al2 = __ffma2_rn(x, x, al2); be2 = __ffma2_rn(y, y, be2); }
     }
-    worst = fmaxf(worst, jacobi_cs(al.x + al.y, be.x + be.y, ga.x + ga.y, c[k], s[k]));
+    const float g = ga.x + ga.y;
+    const float al = WITH_V ? al2.x + al2.y : n2[2 * k], be = WITH_V ? be2.x + be2.y : n2[2 * k + 1];
+    worst = fmaxf(worst, jacobi_cs(al, be, g, c[k], s[k]));
+    if (!WITH_V) {
+      const float tg = (s[k] * f_rcp_fast(c[k])) * g;        // t * gamma (0 when the pair is skipped: s = 0)
+      nn[TMF_PI(2 * k)] = fmaxf(al - tg, 0.0f);
+      nn[TMF_PI(2 * k + 1)] = be + tg;
+    }
+  }
+  if (!WITH_V) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) n2[j] = nn[j];
   }
   rr_apply_rows2(a2, c, s);
   if (WITH_V) rr_apply_rows2(v2, c, s);
@@ -406,9 +435,10 @@ TMF_HD int jacobi_svd8(float* a, float* v, float& unscale) {
       if (WITH_V) v2[8 * rp + j] = make_float2(v[16 * rp + j], v[16 * rp + 8 + j]);
     }
   for (int it = 0; it < TMF_JACOBI_MAX_SWEEPS && more; ++it) {
-    float worst = 0.0f;
+    float worst = 0.0f, n2[8];
+    if (!WITH_V) column_norms2_packed(a2, n2);
 #pragma unroll 1
-    for (int r = 0; r < 7; ++r) worst = fmaxf(worst, jacobi_round2<WITH_V>(a2, v2));
+    for (int r = 0; r < 7; ++r) worst = fmaxf(worst, jacobi_round2<WITH_V>(a2, v2, n2));
     sweeps += (worst > 0.0f) ? 1 : 0;
     more = worst > TMF_JACOBI_DONE;
   }

@@ -149,8 +149,11 @@ __device__ __forceinline__ void load_luma_block(const uint8_t* __restrict__ base
 // ---------------------------------------------------------------------------
 // fused embed, faithful mode (watermarking.py:163-219 in one launch)
 // ---------------------------------------------------------------------------
+#ifndef TMF_FAITHFUL_MIN_CTAS
+#define TMF_FAITHFUL_MIN_CTAS 3
+#endif
 template <int VEC>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, TMF_FAITHFUL_MIN_CTAS)
 k_embed_faithful(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGeom g,
                  const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
   __shared__ float sm[64 * kThreads];

@@ -14,7 +14,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
-VARIANTS = {f"faith_c{c}": {"TMF_FAITHFUL_MIN_CTAS": c} for c in (2, 3)}
+VARIANTS = {f"imadmask{m:x}": {"TMF_EXTRACT_IMAD_MASK": m} for m in (0x8, 0xC, 0xA, 0xE)}
 
 
 def build():

@@ -278,17 +278,29 @@ k_sigma0_faithful(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, B
 #ifndef TMF_BYTE3_IMAD
 #define TMF_BYTE3_IMAD 1
 #endif
+#ifndef TMF_EXTRACT_IMAD_MASK
+#define TMF_EXTRACT_IMAD_MASK 0x8   // bit b set: byte b of a word is extracted on the FMA pipe (IMAD) instead of PRMT
+#endif
 __device__ __forceinline__ float byte_to_magic(const uint32_t (&w)[6], int B) {
   const uint32_t x = w[B >> 2];
+  const int b = B & 3;
   uint32_t m;
-  if ((B & 3) == 3) {
+  if ((TMF_EXTRACT_IMAD_MASK >> b) & 1) {
+    if (b == 3) {
 #if TMF_BYTE3_IMAD
-    asm("mad.hi.u32 %0, %1, 256, 0x4B000000;" : "=r"(m) : "r"(x));
+      asm("mad.hi.u32 %0, %1, 256, 0x4B000000;" : "=r"(m) : "r"(x));
 #else
-    m = __funnelshift_r(x, 0x004B0000u, 24);        // (x >> 24) | 0x4B000000
+      m = __funnelshift_r(x, 0x004B0000u, 24);        // (x >> 24) | 0x4B000000
 #endif
+    } else {
+      uint32_t t;                                      // (x << (24 - 8b)) >> 24, both on the FMA pipe
+      asm("mul.lo.u32 %0, %1, %2;" : "=r"(t) : "r"(x), "r"(1u << (24 - 8 * b)));
+      asm("mad.hi.u32 %0, %1, 256, 0x4B000000;" : "=r"(m) : "r"(t));
+    }
+  } else if (b == 3) {
+    m = __funnelshift_r(x, 0x004B0000u, 24);
   } else {
-    m = __byte_perm(x, 0x4B000000u, 0x7650u | (uint32_t)(B & 3));
+    m = __byte_perm(x, 0x4B000000u, 0x7650u | (uint32_t)b);
   }
   return __uint_as_float(m);
 }

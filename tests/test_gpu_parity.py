@@ -580,3 +580,19 @@ def test_concurrent_sessions_and_determinism():
     assert not errs, errs
     for k in range(8):
         assert np.array_equal(got[k], want[k]), k
+
+
+def test_second_device_and_device_mismatch():
+    x = torch.zeros((16, 16, 3), dtype=torch.uint8, device="cuda:0")
+    with pytest.raises(ValueError, match="alias"):
+        W.embed_tensor(x, torch.zeros((2, 2), dtype=torch.uint8, device="cuda:0"), out=x)
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with pytest.raises(ValueError, match="is on"):
+        W.embed_tensor(x, torch.zeros((2, 2), dtype=torch.uint8, device="cuda:1"))
+    rgb = natural_like(64, 96, 3)
+    wm = np.random.default_rng(0).integers(0, 256, (8, 12), dtype=np.uint8)
+    a = W.embed_tensor(torch.from_numpy(rgb).to("cuda:1"), torch.from_numpy(wm).to("cuda:1"))
+    assert a.device.index == 1 and np.array_equal(a.cpu().numpy(), gpu_embed(rgb, wm, mode=W.DEFAULT_MODE))
+    e = W.extract_tensor(a, torch.from_numpy(rgb).to("cuda:1"))
+    assert e.device.index == 1

@@ -144,6 +144,8 @@ def embed_tensor(rgb, wm, alpha=ALPHA, block_size=BLOCK_SIZE, mode=None, out=Non
     nbh, nbw = h // bs, w // bs
     if not (isinstance(wm, torch.Tensor) and wm.is_cuda and wm.dtype == torch.uint8):
         raise ValueError("wm must be a CUDA uint8 tensor")
+    if wm.device != x.device:
+        raise ValueError(f"wm is on {wm.device} but the images are on {x.device}")
     wm = wm.contiguous()
     if tuple(wm.shape) == (nbh, nbw):
         shared = 1
@@ -156,8 +158,11 @@ def embed_tensor(rgb, wm, alpha=ALPHA, block_size=BLOCK_SIZE, mode=None, out=Non
     else:
         if out.dim() == 3:
             out = out.unsqueeze(0)
-        if out.shape != x.shape or out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous():
-            raise ValueError("out must be a contiguous CUDA uint8 tensor shaped like rgb")
+        if (out.shape != x.shape or out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous()
+                or out.device != x.device):
+            raise ValueError("out must be a contiguous CUDA uint8 tensor shaped like rgb, on the same device")
+        if out.data_ptr() == x.data_ptr():
+            raise ValueError("out must not alias rgb")
     lib = _lib.load()
     with torch.cuda.device(x.device):
         _lib.check(lib.tmf_embed_rgb8(x.data_ptr(), out.data_ptr(), n, h, w, h * w * 3, wm.data_ptr(), shared,

@@ -11,6 +11,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <type_traits>
 
 #include "../../include/tmf_wm.h"
 #include "tmf_math.cuh"
@@ -634,14 +635,20 @@ __device__ __forceinline__ size_t block_origin_n(const BlockGeom& g, long long g
   return (size_t)img * g.img_stride + (size_t)by * N * g.row_pitch + (size_t)bx * (3 * N);
 }
 
-template <int N, bool AL4>
+template <int N, int AL4>
 __device__ __forceinline__ void load_row_rgb255_n(const uint8_t* __restrict__ p, float* r, float* g, float* b) {
   uint8_t raw[3 * N];
-  if (AL4) {
+  if (AL4 == 4) {
 #pragma unroll
     for (int k = 0; k < (3 * N) / 4; ++k) {
       const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p) + k);
       raw[4 * k] = (uint8_t)w; raw[4 * k + 1] = (uint8_t)(w >> 8); raw[4 * k + 2] = (uint8_t)(w >> 16); raw[4 * k + 3] = (uint8_t)(w >> 24);
+    }
+  } else if (AL4 == 2) {
+#pragma unroll
+    for (int k = 0; k < (3 * N) / 2; ++k) {
+      const uint32_t w = __ldg(reinterpret_cast<const uint16_t*>(p) + k);
+      raw[2 * k] = (uint8_t)w; raw[2 * k + 1] = (uint8_t)(w >> 8);
     }
   } else {
 #pragma unroll
@@ -651,7 +658,7 @@ __device__ __forceinline__ void load_row_rgb255_n(const uint8_t* __restrict__ p,
   for (int j = 0; j < N; ++j) { r[j] = (float)raw[3 * j]; g[j] = (float)raw[3 * j + 1]; b[j] = (float)raw[3 * j + 2]; }
 }
 
-template <int N, bool AL4>
+template <int N, int AL4>
 __device__ __forceinline__ void gram_of_block_n(const uint8_t* __restrict__ base, size_t pitch, float* gm) {
 #pragma unroll
   for (int k = 0; k < N * (N + 1) / 2; ++k) gm[k] = 0.0f;
@@ -665,7 +672,7 @@ __device__ __forceinline__ void gram_of_block_n(const uint8_t* __restrict__ base
   }
 }
 
-template <int N, bool AL4>
+template <int N, int AL4>
 __global__ void __launch_bounds__(kThreads)
 k_embed_fast_n(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGeom g,
                const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
@@ -694,10 +701,14 @@ k_embed_fast_n(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, Block
     for (int j = 0; j < N; ++j) y[j] = tmf::luma255_fast(r[j], gg[j], b[j]);
     tmf::embed_row_fast<N>(r, gg, b, y, w, f, c, q);
     uint8_t* d = dst + (size_t)i * g.row_pitch;
-    if (AL4) {
+    if (AL4 == 4) {
 #pragma unroll
       for (int k = 0; k < (3 * N) / 4; ++k)
         reinterpret_cast<uint32_t*>(d)[k] = tmf::pack4_sat_u8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
+    } else if (AL4 == 2) {
+#pragma unroll
+      for (int k = 0; k < (3 * N) / 2; ++k)
+        reinterpret_cast<uint16_t*>(d)[k] = (uint16_t)tmf::pack4_sat_u8(q[2 * k], q[2 * k + 1], 0, 0);
     } else {
 #pragma unroll
       for (int k = 0; k < 3 * N; ++k) d[k] = (uint8_t)min(max(q[k], 0), 255);
@@ -705,14 +716,14 @@ k_embed_fast_n(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, Block
   }
 }
 
-template <int N, bool AL4>
+template <int N, int AL4>
 __device__ __forceinline__ float sigma0_of_block_n(const uint8_t* __restrict__ base, size_t pitch) {
   float gm[N * (N + 1) / 2];
   gram_of_block_n<N, AL4>(base, pitch, gm);
   return tmf::sigma0_from_gram_fast<N>(gm, nullptr);
 }
 
-template <int N, bool AL4>
+template <int N, int AL4>
 __global__ void __launch_bounds__(kThreads)
 k_extract_fast_n(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ orig, uint8_t* __restrict__ out_wm,
                  BlockGeom g, double alpha) {
@@ -725,7 +736,7 @@ k_extract_fast_n(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ or
   out_wm[gb] = (uint8_t)tmf::extract_level(sw, so, alpha);
 }
 
-template <int N, bool AL4>
+template <int N, int AL4>
 __global__ void __launch_bounds__(kThreads)
 k_sigma0_fast_n(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, BlockGeom g) {
   const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -955,21 +966,33 @@ unsigned grid_for(long long items, int per_cta) { return (unsigned)((items + per
 
 
 // dispatch over the block sizes other than 8
-#define TMF_FOR_N(N_, AL4_, CALL)                          \
-  switch (N_) {                                            \
-    case 4:  { constexpr int N = 4;  if (AL4_) { constexpr bool A = true; CALL; } else { constexpr bool A = false; CALL; } } break; \
-    case 6:  { constexpr int N = 6;  constexpr bool A = false; CALL; } break;   /* 18-byte rows: never 4-byte aligned per block */ \
-    case 10: { constexpr int N = 10; constexpr bool A = false; CALL; } break;  \
-    case 12: { constexpr int N = 12; if (AL4_) { constexpr bool A = true; CALL; } else { constexpr bool A = false; CALL; } } break; \
-    case 14: { constexpr int N = 14; constexpr bool A = false; CALL; } break;  \
-    case 16: { constexpr int N = 16; if (AL4_) { constexpr bool A = true; CALL; } else { constexpr bool A = false; CALL; } } break; \
-    default: break;                                        \
-  }
-
-bool aligned4(const BlockGeom& g, const void* p0, const void* p1, const void* p2 = nullptr) {
-  uintptr_t bits = (uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2 | (uintptr_t)g.img_stride | (uintptr_t)g.row_pitch;
-  return (bits & 3) == 0;
+// Dispatch over the block sizes other than 8.  f(N, A) gets integral constants: N = block
+// size, A = access width the block rows allow - 4 bytes (N = 4, 12, 16 with 4-byte aligned
+// rows), 2 bytes (any even N with 2-byte aligned rows), else single bytes.
+template <int N, typename F>
+void with_access_width(int al, bool has4, F&& f) {
+  if (has4 && al == 4) f(std::integral_constant<int, N>{}, std::integral_constant<int, 4>{});
+  else if (al >= 2) f(std::integral_constant<int, N>{}, std::integral_constant<int, 2>{});
+  else f(std::integral_constant<int, N>{}, std::integral_constant<int, 1>{});
 }
+template <typename F>
+void for_block_size(int n, int al, F&& f) {
+  switch (n) {
+    case 4: with_access_width<4>(al, true, f); break;
+    case 6: with_access_width<6>(al, false, f); break;
+    case 10: with_access_width<10>(al, false, f); break;
+    case 12: with_access_width<12>(al, true, f); break;
+    case 14: with_access_width<14>(al, false, f); break;
+    case 16: with_access_width<16>(al, true, f); break;
+    default: break;
+  }
+}
+
+int row_alignment(const BlockGeom& g, const void* p0, const void* p1, const void* p2 = nullptr) {
+  uintptr_t bits = (uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2 | (uintptr_t)g.img_stride | (uintptr_t)g.row_pitch;
+  return (bits & 3) == 0 ? 4 : ((bits & 1) == 0 ? 2 : 1);
+}
+
 
 }  // namespace
 
@@ -1001,8 +1024,9 @@ int tmf_embed_rgb8(const uint8_t* rgb, uint8_t* out, int n, int h, int w, size_t
   cudaStream_t st = (cudaStream_t)stream;
   if (g.total_blocks > 0 && block != 8) {
     const unsigned grid = grid_for(g.total_blocks, kThreads);
-    const bool al4 = aligned4(g, rgb, out);
-    TMF_FOR_N(block, al4, (k_embed_fast_n<N, A><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha)));
+    for_block_size(block, row_alignment(g, rgb, out), [&](auto n_, auto a_) {
+      k_embed_fast_n<decltype(n_)::value, decltype(a_)::value><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha);
+    });
     if (int rc = check_launch("embed kernel launch")) return rc;
   } else if (g.total_blocks > 0) {
     const unsigned grid = grid_for(g.total_blocks, kThreads);
@@ -1041,8 +1065,9 @@ int tmf_extract_rgb8(const uint8_t* wmk_rgb, const uint8_t* orig_rgb, uint8_t* o
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = grid_for(g.total_blocks, kThreads);
   if (block != 8) {
-    const bool al4 = aligned4(g, wmk_rgb, orig_rgb);
-    TMF_FOR_N(block, al4, (k_extract_fast_n<N, A><<<grid, kThreads, 0, st>>>(wmk_rgb, orig_rgb, out_wm, g, alpha)));
+    for_block_size(block, row_alignment(g, wmk_rgb, orig_rgb), [&](auto n_, auto a_) {
+      k_extract_fast_n<decltype(n_)::value, decltype(a_)::value><<<grid, kThreads, 0, st>>>(wmk_rgb, orig_rgb, out_wm, g, alpha);
+    });
     return check_launch("extract kernel launch");
   }
   const int vec = pick_vec(g, wmk_rgb, orig_rgb);
@@ -1072,8 +1097,9 @@ int tmf_sigma0_rgb8(const uint8_t* rgb, float* sigma0, int n, int h, int w, size
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = grid_for(g.total_blocks, kThreads);
   if (block != 8) {
-    const bool al4 = aligned4(g, rgb, rgb);
-    TMF_FOR_N(block, al4, (k_sigma0_fast_n<N, A><<<grid, kThreads, 0, st>>>(rgb, sigma0, g)));
+    for_block_size(block, row_alignment(g, rgb, rgb), [&](auto n_, auto a_) {
+      k_sigma0_fast_n<decltype(n_)::value, decltype(a_)::value><<<grid, kThreads, 0, st>>>(rgb, sigma0, g);
+    });
     return check_launch("sigma0 kernel launch");
   }
   const int vec = pick_vec(g, rgb, rgb);

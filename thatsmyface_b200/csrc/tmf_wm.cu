@@ -1,12 +1,20 @@
 // libtmfwm: sm_100a kernels + C ABI for the DCT+SVD watermark path.
 // See include/tmf_wm.h for the contract and DESIGN.md for the layout/rooflines.
 //
-// Mapping (faithful mode): ONE THREAD OWNS ONE 8x8 BLOCK.  The block, its DCT,
-// the Jacobi-rotated A*V and V all live in that thread's registers with
-// compile-time indices; there are no shuffles, no shared-memory round trips and
-// no redundant (c, s) computation, so every issue slot does useful fp32 work.
-// Adjacent threads own adjacent blocks of one block-row, so a warp's loads of
-// image row r cover 32*24 = 768 contiguous bytes.
+// Mapping, every fused kernel: ONE THREAD OWNS ONE BLOCK; adjacent threads own adjacent
+// blocks of one block-row, so a warp's accesses to image row r cover 32*24 = 768
+// contiguous bytes.  All block arithmetic is in the owning thread's registers with
+// compile-time indices: no shuffles, no exchange between threads, no redundant work.
+//
+//   FAST mode  (tmf_fast.cuh; k_embed_fast / k_extract_fast / k_sigma0_fast, and the
+//              generic-N k_*_fast_n for the UI's other block sizes): two streaming row
+//              passes around a certified power iteration on the 8x8 Gram matrix; packed
+//              fp32 (FFMA2/FADD2/FMUL2); the block itself is never held.
+//   FAITHFUL   (tmf_math.cuh; k_embed_faithful / k_extract_faithful / k_sigma0_faithful):
+//              bit-exact colour, DCT, one-sided Jacobi SVD (A and V in registers, packed
+//              rounds), U diag(S') V^T, IDCT.
+//   taps       k_svd8x8, k_dct8x8, k_rgb2ycc, k_ycc2rgb, k_strip_roundtrip.
+//   host       tmf_ctx_*: H2D / kernel / D2H pipeline over host buffers (end of file).
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>

@@ -6,6 +6,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 from conftest import ROOT
 
@@ -57,3 +58,24 @@ def test_clock_sampler_parses_nvidia_smi_rows():
                (10.2, "0, 1950, 1965, 950.0, 0x0000000000000000, Not Active, Not Active, Not Active, Not Active")]
     out = s.stop(9.9, 10.3)
     assert out["sm_mhz"] == 1950.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+
+
+@pytest.mark.gpu
+def test_b200_arm_prints_one_json_line_with_contract_keys():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--steps", "3", "--warmup", "3",
+                        "--images", "32", "--e2e-images", "8", "--no-cpu-baseline"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["unit"] == "MP/s" and d["value"] > 1000 and d["n_gpus"] == 1 and d["gpu_launches"] == 3
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-3
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] >= 8 * 1080 * 1920 * 3 and e["d2h_bytes_per_step"] == 8 * 1080 * 1920 * 3
+    assert e["matches_device_path"] is True and d["extract"]["watermark_bits_recovered_on_natural_images"] is True
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}

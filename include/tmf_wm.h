@@ -11,6 +11,7 @@
  *   ycbcr_to_rgb()      :53-73                           -> tmf_ycbcr_f32_to_rgb8
  *   apply_dct_to_block / apply_idct_to_block :76-83      -> tmf_dct8x8_f32
  *   np.linalg.svd(block, full_matrices=True) :195,:279   -> tmf_svd8x8_f32
+ *   resize_watermark() after .convert("L")  :105-132     -> tmf_wm_map_l8
  *
  * Conventions
  *   - every pointer is a DEVICE pointer on the current CUDA device unless the
@@ -100,6 +101,23 @@ int tmf_dct8x8_f32(const float* in, float* out, int64_t nblocks, int inverse, vo
  * with the reference (float64 dot, float32 storage, truncating quantiser). */
 int tmf_rgb8_to_ycbcr_f32(const uint8_t* rgb, float* ycc, int64_t npixels, void* stream);
 int tmf_ycbcr_f32_to_rgb8(const float* ycc, uint8_t* rgb, int64_t npixels, void* stream);
+
+/* ---- watermark map on the device -------------------------------------------------------
+ * resize_watermark (watermarking.py:86-132) after `.convert("L")`: PIL's LANCZOS resize of n
+ * mode-"L" images (src_h x src_w bytes each, tightly packed rows, image k at src + k*src_stride)
+ * to the block grid, target_h x target_w = (h/B) x (w/B).  preserve_ratio != 0 keeps the aspect
+ * ratio (sizes truncated as :107-110) and pastes the result centred on a white canvas
+ * (:116-123); 0 stretches to the target (:128-130).  maps: n x target_h x target_w bytes.
+ * Bit-exact with Pillow's 8-bit resampler (Resample.c: float64 Lanczos-3 weights rounded to
+ * 22-bit fixed point, horizontal pass then vertical pass with a uint8 image in between); the
+ * weight tables are built on the host with libm's sin(), the passes run on the device.
+ * `workspace`: device scratch of at least tmf_wm_map_workspace_bytes(...) bytes, 16-byte
+ * aligned, caller-owned, reusable once the work on `stream` has completed.
+ * Not supported (TMF_ERR_BAD_ARG): a resized side of 0 pixels (PIL raises too), sources more
+ * than 100x taller than wide (PIL switches pass order there), src_w above 49136. */
+size_t tmf_wm_map_workspace_bytes(int n, int src_h, int src_w, int target_h, int target_w, int preserve_ratio);
+int tmf_wm_map_l8(const uint8_t* src, int n, int src_h, int src_w, size_t src_stride, uint8_t* maps, int target_h,
+                  int target_w, int preserve_ratio, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- host-buffer pipeline -------------------------------------------------------------
  * The per-image loop of the embed page (embed_watermark_page.py:492-558) as one call on

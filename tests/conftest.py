@@ -15,7 +15,8 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+    """Embed/extract cases (one image each); wm_map_cases.npz belongs to tests/test_wm_map.py."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("wm_map_"))
 
 
 @pytest.fixture(scope="session")

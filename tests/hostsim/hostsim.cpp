@@ -7,6 +7,7 @@
 #include <cstring>
 #include "../../thatsmyface_b200/csrc/tmf_math.cuh"
 #include "../../thatsmyface_b200/csrc/tmf_fast.cuh"
+#include "../../thatsmyface_b200/csrc/tmf_resize.cuh"
 
 using namespace tmf;
 
@@ -239,4 +240,47 @@ int hostsim_rgb2ycc(const uint8_t* rgb, float* ycc, int64_t npx) {
   }
   return 0;
 }
+}
+
+// tmf_wm_map_l8's arithmetic on the host: the library's own table builder and per-sample
+// function (tmf_resize.cuh) driven the way the two kernels drive them.
+extern "C" int hostsim_wm_map_l8(const uint8_t* src, int src_h, int src_w, uint8_t* map, int target_h, int target_w,
+                                 int preserve_ratio) {
+  const MapGeometry g = watermark_map_geometry(src_h, src_w, target_h, target_w, preserve_ratio);
+  if (g.new_h <= 0 || g.new_w <= 0) return -1;
+  const bool need_h = g.new_w != src_w, need_v = g.new_h != src_h;
+  AxisTable th, tv;
+  int row0 = 0, rows = src_h;
+  if (need_v) {
+    lanczos_axis_table(src_h, g.new_h, tv);
+    if (need_h) {
+      row0 = tv.bounds[0];
+      rows = tv.bounds[2 * (g.new_h - 1)] + tv.bounds[2 * (g.new_h - 1) + 1] - row0;
+      for (int i = 0; i < g.new_h; ++i) tv.bounds[2 * i] -= row0;
+    }
+  }
+  std::vector<uint8_t> tmp;
+  const uint8_t* in = src;
+  int pitch = src_w;
+  if (need_h) {
+    lanczos_axis_table(src_w, g.new_w, th);
+    tmp.resize((size_t)rows * g.new_w);
+    for (int r = 0; r < rows; ++r)
+      for (int xx = 0; xx < g.new_w; ++xx)
+        tmp[(size_t)r * g.new_w + xx] = resample_sample(src + (size_t)(row0 + r) * src_w + th.bounds[2 * xx], 1,
+                                                        &th.kk[(size_t)xx * th.ksize], 1, th.bounds[2 * xx + 1]);
+    in = tmp.data();
+    pitch = g.new_w;
+  }
+  for (int y = 0; y < target_h; ++y)
+    for (int x = 0; x < target_w; ++x) {
+      const int yy = y - g.paste_y, xx = x - g.paste_x;
+      uint8_t v = 255;
+      if (yy >= 0 && yy < g.new_h && xx >= 0 && xx < g.new_w)
+        v = need_v ? resample_sample(in + (size_t)tv.bounds[2 * yy] * pitch + xx, pitch, &tv.kk[(size_t)yy * tv.ksize], 1,
+                                     tv.bounds[2 * yy + 1])
+                   : in[(size_t)yy * pitch + xx];
+      map[(size_t)y * target_w + x] = v;
+    }
+  return 0;
 }

@@ -10,7 +10,7 @@ HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
 SO = os.path.join(HERE, "_hostsim.so")
 SRC = os.path.join(HERE, "hostsim.cpp")
 CSRC = os.path.join(os.path.dirname(HERE), "..", "thatsmyface_b200", "csrc")
-HDRS = [os.path.join(CSRC, "tmf_math.cuh"), os.path.join(CSRC, "tmf_fast.cuh")]
+HDRS = [os.path.join(CSRC, n) for n in ("tmf_math.cuh", "tmf_fast.cuh", "tmf_resize.cuh")]
 _lib = None
 
 
@@ -87,4 +87,14 @@ def extract_n(a, b, alpha, bs):
     h, w = a.shape[:2]
     out = np.zeros((h // bs, w // bs), np.uint8)
     assert lib().hostsim_extract_n(_p(a), _p(b), _p(out), h, w, C.c_double(alpha), bs) == 0
+    return out
+
+
+def wm_map_l8(src, target_h, target_w, preserve_ratio=False):
+    src = np.ascontiguousarray(src, np.uint8)
+    out = np.empty((target_h, target_w), np.uint8)
+    rc = lib().hostsim_wm_map_l8(_p(src), src.shape[0], src.shape[1], _p(out), target_h, target_w,
+                                 1 if preserve_ratio else 0)
+    if rc:
+        raise ValueError("height and width must be > 0")
     return out

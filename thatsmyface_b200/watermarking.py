@@ -13,7 +13,8 @@ reference function         lines                                  here
 ``ycbcr_to_rgb``            ``:53-73``                             ``tmf_ycbcr_f32_to_rgb8``
 ``apply_dct_to_block``      ``:76-78``                             ``tmf_dct8x8_f32``
 ``apply_idct_to_block``     ``:81-83``                             ``tmf_dct8x8_f32`` (inverse)
-``resize_watermark``        ``:86-132``                            host (PIL), unchanged semantics
+``resize_watermark``        ``:86-132``                            host (PIL), unchanged semantics;
+                                                                   ``tmf_wm_map_l8`` on device (batches)
 ``embed_watermark``         ``:135-221``                           ``tmf_embed_rgb8``
 ``extract_watermark``       ``:224-294``                           ``tmf_extract_rgb8``
 =========================  =====================================  ====================
@@ -25,6 +26,7 @@ compute entry point raises ``RuntimeError``.
 from __future__ import annotations
 
 import collections
+import concurrent.futures
 import hashlib
 import io
 import os
@@ -43,7 +45,7 @@ __all__ = [
     "apply_idct_to_block", "resize_watermark", "embed_watermark", "extract_watermark",
     "embed_tensor", "extract_tensor", "sigma0_tensor", "svd8x8", "dct8x8",
     "embed_watermark_batch", "extract_watermark_batch", "watermark_map", "clear_watermark_cache",
-    "prepare_for_decoding",
+    "prepare_for_decoding", "watermark_map_tensor", "watermark_maps",
 ]
 
 #: mode used when neither ``custom_settings["mode"]`` nor an explicit argument says otherwise.
@@ -376,6 +378,75 @@ def watermark_map(watermark_data, target_height, target_width, preserve_ratio=Fa
         t = torch.from_numpy(entry["host"]).to(dev)
         entry[dkey] = t
     return t
+
+
+def watermark_map_tensor(sources, target_height, target_width, preserve_ratio=False, out=None):
+    """``resize_watermark`` (watermarking.py:86-132) after ``.convert("L")`` on the device
+    (``tmf_wm_map_l8``): ``sources`` is a CUDA uint8 tensor ``(n, sh, sw)``
+    or ``(sh, sw)`` of mode-"L" watermark images of one size; returns CUDA uint8
+    ``(n, target_height, target_width)`` (or 2-D for a 2-D input), bit-identical to what PIL's
+    LANCZOS resize + centred paste on white produce.  For batches whose images carry DIFFERENT
+    watermarks; for one shared watermark ``watermark_map`` (cached) is all that is needed."""
+    torch = _torch()
+    if not (isinstance(sources, torch.Tensor) and sources.is_cuda and sources.dtype == torch.uint8):
+        raise ValueError("sources must be a CUDA uint8 tensor")
+    squeeze = sources.dim() == 2
+    src = (sources.unsqueeze(0) if squeeze else sources).contiguous()
+    if src.dim() != 3:
+        raise ValueError(f"sources must have shape (n, h, w) or (h, w), got {tuple(sources.shape)}")
+    n, sh, sw = (int(v) for v in src.shape)
+    th, tw, pr = int(target_height), int(target_width), 1 if preserve_ratio else 0
+    lib = _lib.load()
+    with torch.cuda.device(src.device):
+        need = lib.tmf_wm_map_workspace_bytes(n, sh, sw, th, tw, pr)
+        if out is None:
+            maps = torch.empty((n, max(th, 0), max(tw, 0)), dtype=torch.uint8, device=src.device)
+        else:
+            maps = out.unsqueeze(0) if out.dim() == 2 else out
+            if not (maps.is_cuda and maps.device == src.device and maps.dtype == torch.uint8
+                    and maps.is_contiguous() and tuple(maps.shape) == (n, th, tw)):
+                raise ValueError(f"out must be a contiguous CUDA uint8 tensor of shape {(n, th, tw)} on {src.device}")
+        work = torch.empty(max(int(need), 16), dtype=torch.uint8, device=src.device)
+        _lib.check(lib.tmf_wm_map_l8(src.data_ptr(), n, sh, sw, sh * sw, maps.data_ptr(), th, tw, pr,
+                                     work.data_ptr(), work.numel(), _stream_ptr(torch)))
+        work.record_stream(torch.cuda.current_stream())
+    if out is not None:
+        return out
+    return maps[0] if squeeze else maps
+
+
+def watermark_maps(watermarks, target_height, target_width, preserve_ratio=False, device=None, workers=8):
+    """Per-image watermark maps for a batch: ``watermarks`` is a sequence of PNG ``bytes`` or PIL
+    images (one per image, what ``embed_watermark`` takes).  Decoding and ``.convert("L")`` stay
+    on the host (PIL, in a small thread pool); sources of equal size are stacked, uploaded once
+    and resized together by ``watermark_map_tensor``.  Returns CUDA uint8
+    ``(len(watermarks), target_height, target_width)`` - the ``wm`` argument of ``embed_tensor``."""
+    torch = _torch()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+    def decode(wm):
+        img = Image.open(io.BytesIO(bytes(wm))) if isinstance(wm, (bytes, bytearray)) else wm
+        img = img.convert("L")
+        w, h = img.size
+        return np.frombuffer(img.tobytes(), dtype=np.uint8).reshape(h, w)
+
+    items = list(watermarks)
+    if len(items) > 1 and workers > 1:
+        with concurrent.futures.ThreadPoolExecutor(min(int(workers), len(items))) as pool:
+            decoded = list(pool.map(decode, items))
+    else:
+        decoded = [decode(w) for w in items]
+    out = torch.empty((len(items), int(target_height), int(target_width)), dtype=torch.uint8, device=dev)
+    by_shape = collections.defaultdict(list)
+    for i, a in enumerate(decoded):
+        by_shape[a.shape].append(i)
+    for shape, idx in by_shape.items():
+        stack = torch.from_numpy(np.stack([decoded[i] for i in idx])).to(dev, non_blocking=False)
+        maps = watermark_map_tensor(stack, target_height, target_width, preserve_ratio)
+        if len(by_shape) == 1:
+            return maps
+        out[torch.as_tensor(idx, device=dev)] = maps
+    return out
 
 
 def clear_watermark_cache():

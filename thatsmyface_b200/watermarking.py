@@ -376,6 +376,8 @@ def watermark_map(watermark_data, target_height, target_width, preserve_ratio=Fa
     t = entry.get(dkey)
     if t is None:
         t = torch.from_numpy(entry["host"]).to(dev)
+        # published to other threads / streams (page_loop lanes): make sure the copy has landed
+        torch.cuda.current_stream(dev).synchronize()
         entry[dkey] = t
     return t
 

@@ -127,6 +127,16 @@ BENCH(k_conv_magic_x4, CONV_DECL, FF8 CV_MAGIC(u0) CV_MAGIC(u1) CV_MAGIC(u2) CV_
 BENCH(k_conv_i2f_x4, CONV_DECL, FF8 CV_I2F(u0) CV_I2F(u1) CV_I2F(u2) CV_I2F(u3), CONV_SINK)
 BENCH(k_conv_mixed_3m1i, CONV_DECL, FF8 CV_MAGIC(u0) CV_MAGIC(u1) CV_MAGIC(u2) CV_I2F(u3), CONV_SINK)
 
+#define OP_DP2A(x) asm volatile("dp2a.lo.u32.u32 %0, %1, %0, %2;" : "+r"(x) : "r"(kb | 0x024B012Bu), "r"(kc));
+BENCH(k_dp2a, U8, R8(OP_DP2A), SINKU)
+#define OP_DP4A(x) asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(kb | 0x01020304u), "r"(kc));
+BENCH(k_dp4a, U8, R8(OP_DP4A), SINKU)
+#define OP_DP(u) asm volatile("dp2a.lo.u32.u32 %0, %1, %0, %2;" : "+r"(u) : "r"(kc | 0x024B012Bu), "r"(kc));
+#define DP8 OP_DP(u0) OP_DP(u1) OP_DP(u2) OP_DP(u3) OP_DP(u4) OP_DP(u5) OP_DP(u6) OP_DP(u7)
+#define DP4 OP_DP(u0) OP_DP(u1) OP_DP(u2) OP_DP(u3)
+BENCH(k_mix_8ffma_8dp2a, MIXDECL, FF8 DP8, MIXSINK)
+BENCH(k_mix_8ffma_4dp2a, MIXDECL, FF8 DP4, MIXSINK)
+BENCH(k_mix_4dp2a_4prmt, MIXDECL, DP4 OP_PR(u4) OP_PR(u5) OP_PR(u6) OP_PR(u7), MIXSINK)
 struct T { const char* name; void (*k)(long long*, float*); int ops; };
 
 int main() {
@@ -154,6 +164,9 @@ int main() {
     {"conv: 8 ffma + 2 x (i2f.u8 byte1, +fadd acc, +iadd)", k_conv_i2f_x2, 1},
     {"conv: 8 ffma + 4 x magic", k_conv_magic_x4, 1}, {"conv: 8 ffma + 4 x i2f.u8", k_conv_i2f_x4, 1},
     {"conv: 8 ffma + 3 x magic + 1 x i2f.u8", k_conv_mixed_3m1i, 1},
+    {"dp2a.lo.u32.u32", k_dp2a, 8}, {"dp4a.u32.u32", k_dp4a, 8},
+    {"mix: 8 ffma + 8 dp2a", k_mix_8ffma_8dp2a, 1}, {"mix: 8 ffma + 4 dp2a", k_mix_8ffma_4dp2a, 1},
+    {"mix: 4 dp2a + 4 prmt", k_mix_4dp2a_4prmt, 1},
     {"mix: 4 ffma2 + 8 prmt (same flops)", k_mix_4ffma2_8prmt, 1}, {"mix: 4 ffma2 + 4 prmt", k_mix_4ffma2_4prmt, 1},
   };
   printf("device SMs=%d clockRate=%d kHz; rows are iterations of the listed sequence per clk per SM (1024 thr/SM)\n", sms, clk_khz);

@@ -77,7 +77,8 @@ static void gram_of_block(const uint8_t* rgb, int w, int by, int bx, float* gm, 
   for (int i = 0; i < 8; ++i) {
     float r[8], g[8], b[8], y[8];
     row_rgb255(rgb, w, by * 8 + i, bx * 8, r, g, b);
-    for (int j = 0; j < 8; ++j) y[j] = luma255_fast(r[j], g[j], b[j]);
+    // the N = 8 kernels carry the exact integer luma 299 r + 587 g + 114 b (IDP.2A on the device)
+    for (int j = 0; j < 8; ++j) y[j] = luma1000_exact((uint32_t)r[j], (uint32_t)g[j], (uint32_t)b[j]);
     if (keep) for (int j = 0; j < 8; ++j) keep[8 * i + j] = y[j];
     gram_accumulate_row(y, gm);
   }
@@ -97,7 +98,7 @@ int hostsim_embed_fast(const uint8_t* rgb, uint8_t* out, int h, int w, const uin
       float gm[36], wv[8], f, c, lum[64];
       gram_of_block(rgb, w, by, bx, gm, lum);
       int it;
-      float sig = embed_block_scalars_fast(gm, alpha, wm[by * nbw + bx], wv, f, c, &it);
+      float sig = embed_block_scalars_fast(gm, alpha, wm[by * nbw + bx], wv, f, c, &it, TMF_LUMA1000_UNIT);
       if (sigma_out) sigma_out[by * nbw + bx] = sig;
       if (sweeps_out) sweeps_out[by * nbw + bx] = it;
       for (int i = 0; i < 8; ++i) {
@@ -121,9 +122,9 @@ int hostsim_extract_fast(const uint8_t* wmk, const uint8_t* orig, uint8_t* out, 
     for (int bx = 0; bx < nbw; ++bx) {
       float gm[36];
       gram_of_block(wmk, w, by, bx, gm);
-      float sw = sigma0_from_gram_fast(gm, nullptr);
+      float sw = sigma0_from_gram_fast(gm, nullptr, TMF_LUMA1000_UNIT);
       gram_of_block(orig, w, by, bx, gm);
-      float so = sigma0_from_gram_fast(gm, nullptr);
+      float so = sigma0_from_gram_fast(gm, nullptr, TMF_LUMA1000_UNIT);
       out[by * nbw + bx] = (uint8_t)extract_level(sw, so, alpha);
     }
   return 0;

@@ -186,9 +186,12 @@ TMF_HD int top_pair(float* m, float* w, float& ww, float& mu) {
 // all-zero block (LAPACK's U = V = I puts the mark on the DC coefficient, which
 // is the constant 1/N pattern in the spatial domain).  Returns sigma0 in the
 // reference's units (luma in [0, 1]).
+//
+// `unit` = reference luma units per unit of the Gram's luma: 1/255 for luma in 0..255
+// (luma255_fast), 1/255000 for the exact integer luma 299 r + 587 g + 114 b (luma1000_exact).
 template <int N = 8>
 TMF_HD float embed_block_scalars_fast(float* g, double alpha, uint32_t wm_u8, float* w, float& f, float& c,
-                                      int* iters) {
+                                      int* iters, float unit = 1.0f / 255.0f) {
   constexpr int NS = N * (N + 1) / 2;
   const float tr = sym_trace<N>(g);
   float sig255 = 0.0f, ww = (float)N;
@@ -205,7 +208,7 @@ TMF_HD float embed_block_scalars_fast(float* g, double alpha, uint32_t wm_u8, fl
 #pragma unroll
     for (int i = 0; i < N; ++i) w[i] = 1.0f;
   }
-  const float sig = sig255 * (1.0f / 255.0f);
+  const float sig = sig255 * unit;
   const float d255 = (modulate_sigma0(sig, alpha, wm_u8) - sig) * 255.0f;   // watermarking.py:198
   if (tr > 0.0f) { f = f_div(d255, sig255 * ww); c = 0.0f; }
   else { f = 0.0f; c = d255 * (1.0f / (float)N); }
@@ -214,7 +217,7 @@ TMF_HD float embed_block_scalars_fast(float* g, double alpha, uint32_t wm_u8, fl
 
 // Largest singular value (reference units) from the pass-1 Gram matrix (destroyed).
 template <int N = 8>
-TMF_HD float sigma0_from_gram_fast(float* g, int* iters) {
+TMF_HD float sigma0_from_gram_fast(float* g, int* iters, float unit = 1.0f / 255.0f) {
   constexpr int NS = N * (N + 1) / 2;
   const float tr = sym_trace<N>(g);
   if (iters) *iters = 0;
@@ -225,8 +228,15 @@ TMF_HD float sigma0_from_gram_fast(float* g, int* iters) {
   float w[N], ww, mu;
   const int it = top_pair<false, N>(g, w, ww, mu);
   if (iters) *iters = it;
-  return f_sqrt(tr * mu) * (1.0f / 255.0f);
+  return f_sqrt(tr * mu) * unit;
 }
+
+// The reference's luma weights are three-decimal constants (watermarking.py:37), so
+// 1000 * 255 * Y = 299 r + 587 g + 114 b is an exact integer below 2^18: the N = 8 kernels
+// compute it with two IDP.2A per pixel straight from the packed bytes (no byte extraction, no
+// rounding) and carry the Gram matrix and the luma stash in these units.
+TMF_HD float luma1000_exact(uint32_t r, uint32_t g, uint32_t b) { return (float)(299u * r + 587u * g + 114u * b); }
+#define TMF_LUMA1000_UNIT (1.0f / 255000.0f)
 
 // --- fp32 colour in 0..255 units -------------------------------------------
 // luma of watermarking.py:37-45 times 255

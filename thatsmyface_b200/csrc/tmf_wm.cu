@@ -387,8 +387,57 @@ __device__ __forceinline__ float2 bytes_to_float2(const uint32_t (&w)[6], int B)
   return __fadd2_rn(make_float2(byte_to_magic(w, B), byte_to_magic(w, B + 3)), bc2(-8388608.0f));
 }
 
-// luma of the 8 pixels of a row as four pairs; same values as tmf::luma255_fast
+// Exact integer luma 299 r + 587 g + 114 b (tmf::luma1000_exact) of the 8 pixels of a row
+// without extracting a single byte: a pixel's three bytes sit in one or two of the row's six
+// words, and two IDP.2A (16-bit weights x bytes 0-1 or 2-3 of a word, accumulate) cover them
+// whatever the phase.  The accumulator starts at 0x4B000000, so the result already is the
+// bit pattern of the float 2^23 + luma (luma < 2^18), and one packed FADD per pixel pair
+// removes the 2^23.  Against PRMT extraction + fp32 FMAs this halves the issue cost of
+// pass 1's colour step and moves it from the ALU pipe (the busier one) to the FMA pipe.
+#ifndef TMF_LUMA_IDP
+#define TMF_LUMA_IDP 1
+#endif
+#if TMF_LUMA_IDP && !TMF_USE_F32X2
+#error "TMF_LUMA_IDP needs the packed (TMF_USE_F32X2) row code"
+#endif
+#if TMF_LUMA_IDP
+#define TMF_LUMA_UNIT TMF_LUMA1000_UNIT
+#else
+#define TMF_LUMA_UNIT (1.0f / 255.0f)
+#endif
+__device__ __forceinline__ uint32_t dp2a_lo(uint32_t bytes, uint32_t w16x2, uint32_t acc) {
+  uint32_t d;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w16x2), "r"(bytes), "r"(acc));
+  return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi(uint32_t bytes, uint32_t w16x2, uint32_t acc) {
+  uint32_t d;
+  asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w16x2), "r"(bytes), "r"(acc));
+  return d;
+}
+// magic float 2^23 + (299 r + 587 g + 114 b) of pixel j of the row
+__device__ __forceinline__ float pixel_luma_magic(const uint32_t (&w)[6], int j) {
+  constexpr uint32_t kRG = 299u | (587u << 16), kB_ = 114u, k_R = 299u << 16, kGB = 587u | (114u << 16);
+  const int k = (3 * j) >> 2;
+  uint32_t m;
+  switch ((3 * j) & 3) {
+    case 0: m = dp2a_hi(w[k], kB_, dp2a_lo(w[k], kRG, 0x4B000000u)); break;          // [r g b .]
+    case 1: m = dp2a_hi(w[k], kGB, dp2a_lo(w[k], k_R, 0x4B000000u)); break;          // [. r g b]
+    case 2: m = dp2a_lo(w[k + 1], kB_, dp2a_hi(w[k], kRG, 0x4B000000u)); break;      // [. . r g][b . . .]
+    default: m = dp2a_lo(w[k + 1], kGB, dp2a_hi(w[k], k_R, 0x4B000000u)); break;     // [. . . r][g b . .]
+  }
+  return __uint_as_float(m);
+}
+
+// luma of the 8 pixels of a row as four pairs; same values as tmf::luma1000_exact
+// (TMF_LUMA_IDP) or tmf::luma255_fast
 __device__ __forceinline__ void row_luma2(const uint32_t (&w)[6], float2 (&y2)[4]) {
+#if TMF_LUMA_IDP
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+    y2[p] = __fadd2_rn(make_float2(pixel_luma_magic(w, 2 * p), pixel_luma_magic(w, 2 * p + 1)), bc2(-8388608.0f));
+  return;
+#endif
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     const int B = 6 * p;                 // byte offset of pixel 2p
@@ -555,7 +604,7 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
   if (mark != 0) {
     float gm[36];
     gram_of_block<VEC, true>(src, g.row_pitch, gm, col);
-    tmf::embed_block_scalars_fast(gm, alpha, mark, w, f, c, nullptr);
+    tmf::embed_block_scalars_fast(gm, alpha, mark, w, f, c, nullptr, TMF_LUMA_UNIT);
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) w[i] = 0.0f;
@@ -609,7 +658,7 @@ k_extract_fast(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ orig
   for (int which = 0; which < 2; ++which) {
     float gm[36];
     gram_of_block<VEC, false>((which == 0 ? wmk : orig) + org, g.row_pitch, gm);
-    const float sg = tmf::sigma0_from_gram_fast(gm, nullptr);
+    const float sg = tmf::sigma0_from_gram_fast(gm, nullptr, TMF_LUMA_UNIT);
     if (which == 0) sw = sg; else so = sg;
   }
   out_wm[gb] = (uint8_t)tmf::extract_level(sw, so, alpha);
@@ -625,7 +674,7 @@ k_sigma0_fast(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, Block
   float gm[36];
   prefetch_block_rows(rgb + org, g.row_pitch);
   gram_of_block<VEC, false>(rgb + org, g.row_pitch, gm);
-  sigma0[gb] = tmf::sigma0_from_gram_fast(gm, nullptr);
+  sigma0[gb] = tmf::sigma0_from_gram_fast(gm, nullptr, TMF_LUMA_UNIT);
 }
 
 

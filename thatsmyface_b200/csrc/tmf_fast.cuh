@@ -112,7 +112,8 @@ TMF_HD float dot8(const float* a, const float* b) { return dotn<8>(a, b); }
 //   one squaring, near-tied ones a few; the bound is rigorous for any gap.
 //
 // On return w (not normalised, ww = w.w) spans v0 to `tol` and mu ~ mu_0 of the ORIGINAL
-// m to ~1e-7 (mu_l = sqrt(mu_{l+1} tr(M_l^2)) unwinds the squarings).  Returns
+// m to ~1e-7 (mu_l = sqrt(mu_{l+1} tr(M_l^2)) unwinds the squarings; carried forward as one
+// running product so that no per-level array - local memory - is needed).  Returns
 // products + 100 * squarings.
 #define TMF_FAST_TOL_VEC_EMBED 1.0e-6f     // u0 v0^T itself is used
 #define TMF_FAST_TOL_VEC_EXTRACT 3.0e-4f   // sigma0 only: second order in the vector error
@@ -123,7 +124,8 @@ TMF_HD int top_pair(float* m, float* w, float& ww, float& mu) {
   constexpr int NS = N * (N + 1) / 2;
   const float tol = EMBED ? TMF_FAST_TOL_VEC_EMBED : TMF_FAST_TOL_VEC_EXTRACT;
   const float theta0 = f_sqrt((float)(N - 1));
-  float x[N], y[N], tr2[TMF_FAST_MAX_LEVELS];
+  float x[N], y[N];
+  float unwind = 1.0f;   // prod_l tr(M_l^2)^(1/2^(l+1)): mu_0 = unwind * mu_L^(1/2^L), kept in a register
   float theta = theta0;
   int level = 0, products = 0;
 #pragma unroll
@@ -160,7 +162,11 @@ TMF_HD int top_pair(float* m, float* w, float& ww, float& mu) {
     // square in place: M <- M^2 / tr(M^2)
     float p[NS];
     const float t = sym_square<N>(m, p);
-    tr2[level] = t;
+    {
+      float r = t;                        // t^(1/2^(level+1)); levels are few, square roots cheap
+      for (int k = 0; k <= level; ++k) r = f_sqrt(r);
+      unwind *= r;
+    }
     const float inv = f_rcp_fast(t);
 #pragma unroll
     for (int k = 0; k < NS; ++k) m[k] = p[k] * inv;
@@ -175,7 +181,8 @@ TMF_HD int top_pair(float* m, float* w, float& ww, float& mu) {
   for (int i = 0; i < N; ++i) w[i] = y[i];
   ww = yy;
   mu = yy * f_rcp_fast(xy);              // (w_J.w_J)/(w_{J-1}.w_J) <= mu_0 of the current level
-  for (int l = level - 1; l >= 0; --l) mu = f_sqrt(mu * tr2[l]);
+  for (int l = 0; l < level; ++l) mu = f_sqrt(mu);
+  mu *= unwind;
   return products + 100 * level;
 }
 
@@ -246,12 +253,23 @@ TMF_HD float luma255_fast(float r, float g, float b) {
 // watermarking.py:37-48 and :58-73 composed: the reference maps (r, g, b) to
 // (y, cb, cr), adds the mark to y, and maps back with a matrix that is not the
 // exact inverse, so a pixel comes back as  M k + d  with  M = Ti T  (the two
-// reference matrices multiplied out in float64) and d the luma change of that
-// pixel.  All in 0..255 units; the caller clips and truncates.
+// reference matrices multiplied out; every entry is an exact multiple of 1e-6) and d
+// the luma change of that pixel.  M = I + E and E's rows sum to zero (a grey pixel maps
+// to itself), so with u = r - g, v = b - g (exact):
+//     out_c = k_c + s_c,   s_c = E_c0 u + E_c2 v + d        (|s_c| is small)
+// All in 0..255 units; the caller floors k_c + s_c (exactly, floor_sum_to_int) and clips.
+TMF_HD void rgb255_delta_fast(float r, float g, float b, float d, float& sR, float& sG, float& sB) {
+  const float u = r - g, v = b - g;
+  sR = fmaf(5.00e-4f, u, fmaf(3.57e-4f, v, d));
+  sG = fmaf(1.36e-4f, u, fmaf(-1.66e-4f, v, d));
+  sB = fmaf(-6.37e-4f, u, fmaf(5.00e-4f, v, d));
+}
+// the same pixel as one value per channel (k_c + s_c rounded to fp32): kept for callers that
+// want the unquantised colour
 TMF_HD void rgb255_out_fast(float r, float g, float b, float d, float& R, float& G, float& B) {
-  R = fmaf(1.0005f, r, fmaf(-8.57e-4f, g, fmaf(3.57e-4f, b, d)));
-  G = fmaf(1.36e-4f, r, fmaf(1.00003f, g, fmaf(-1.66e-4f, b, d)));
-  B = fmaf(-6.37e-4f, r, fmaf(1.37e-4f, g, fmaf(1.0005f, b, d)));
+  float sR, sG, sB;
+  rgb255_delta_fast(r, g, b, d, sR, sG, sB);
+  R = r + sR; G = g + sG; B = b + sB;
 }
 
 // floor(x) as a signed integer for |x| < 2^22 with one FADD.RM (round toward
@@ -264,6 +282,17 @@ TMF_HD int floor_to_int(float x) {
   return __float_as_int(__fadd_rd(x, 12582912.0f)) - 0x4B400000;
 #else
   return (int)floorf(x);
+#endif
+}
+
+// floor(k + s) for an integer-valued k in [0, 2^22) and |s| < 2^22, with no rounding of the
+// sum: k sits on the quantiser's bias (1.5*2^23 + k is exact) and FADD.RM of s onto it is
+// 1.5*2^23 + floor(k + s).
+TMF_HD int floor_sum_to_int(float k, float s) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(__fadd_rd(s, 12582912.0f + k)) - 0x4B400000;
+#else
+  return (int)floor((double)k + (double)s);
 #endif
 }
 
@@ -289,11 +318,11 @@ TMF_HD void embed_row_fast(const float* r, const float* g, const float* b, const
   const float du = fmaf(f, dotn<N>(y, w), c);
 #pragma unroll
   for (int j = 0; j < N; ++j) {
-    float R, G, B;
-    rgb255_out_fast(r[j], g[j], b[j], du * w[j], R, G, B);
-    q[3 * j] = floor_to_int(R);
-    q[3 * j + 1] = floor_to_int(G);
-    q[3 * j + 2] = floor_to_int(B);
+    float sR, sG, sB;
+    rgb255_delta_fast(r[j], g[j], b[j], du * w[j], sR, sG, sB);
+    q[3 * j] = floor_sum_to_int(r[j], sR);
+    q[3 * j + 1] = floor_sum_to_int(g[j], sG);
+    q[3 * j + 2] = floor_sum_to_int(b[j], sB);
   }
 }
 

@@ -101,21 +101,42 @@ __device__ __forceinline__ void store_row24(uint8_t* __restrict__ p, const uint3
 // byte B (0..23) of a 24-byte row held in six words
 #define TMF_BYTE(w, B) (((w)[(B) >> 2] >> (8 * ((B)&3))) & 0xffu)
 
+// n / d for n < 2^31 as one 32x32->64 multiply and a shift: mul = ceil(2^shift / d),
+// shift = 31 + ceil(log2 d) (exact: the error term n*e/(d*2^shift) stays below 1/d).
+struct FastDiv {
+  uint32_t mul, shift;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  f.shift = 31 + s;
+  f.mul = (uint32_t)(((1ull << f.shift) + d - 1) / d);
+  return f;
+}
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, FastDiv f) {
+  return (uint32_t)(((unsigned long long)n * f.mul) >> f.shift);
+}
+
 struct BlockGeom {
   int h, w, nbh, nbw;
   int bs;                     // block size (8 on the optimised path)
   long long blocks_per_img;   // nbh * nbw
-  long long total_blocks;     // n * blocks_per_img
+  long long total_blocks;     // n * blocks_per_img  (< 2^31, make_geom)
   size_t img_stride;          // bytes between images
   size_t row_pitch;           // 3 * w
+  FastDiv div_bpi, div_nbw;   // block index -> (image, block row, block column) without divisions
 };
 
 __device__ __forceinline__ size_t block_origin(const BlockGeom& g, long long gb, long long& img, int& by, int& bx) {
-  img = gb / g.blocks_per_img;
-  const int r = (int)(gb - img * g.blocks_per_img);
-  by = r / g.nbw;
-  bx = r - by * g.nbw;
-  return (size_t)img * g.img_stride + (size_t)by * 8 * g.row_pitch + (size_t)bx * 24;
+  const uint32_t n = (uint32_t)gb;
+  const uint32_t im = fastdiv(n, g.div_bpi);
+  const uint32_t r = n - im * (uint32_t)g.blocks_per_img;
+  const uint32_t y = fastdiv(r, g.div_nbw);
+  img = im;
+  by = (int)y;
+  bx = (int)(r - y * (uint32_t)g.nbw);
+  return (size_t)im * g.img_stride + (size_t)y * 8 * g.row_pitch + (size_t)bx * 24;
 }
 
 // Ask for all 8 rows of a block up front.  The row loops below are rolled (small
@@ -291,6 +312,8 @@ k_sigma0_faithful(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, B
 #ifndef TMF_EXTRACT_IMAD_MASK
 #define TMF_EXTRACT_IMAD_MASK 0x8   // bit b set: byte b of a word is extracted on the FMA pipe (IMAD) instead of PRMT
 #endif
+// MAGIC = 0x4B000000 (2^23) or 0x4B400000 (1.5 * 2^23, the floor bias of the quantiser).
+template <uint32_t MAGIC = 0x4B000000u>
 __device__ __forceinline__ float byte_to_magic(const uint32_t (&w)[6], int B) {
   const uint32_t x = w[B >> 2];
   const int b = B & 3;
@@ -298,19 +321,19 @@ __device__ __forceinline__ float byte_to_magic(const uint32_t (&w)[6], int B) {
   if ((TMF_EXTRACT_IMAD_MASK >> b) & 1) {
     if (b == 3) {
 #if TMF_BYTE3_IMAD
-      asm("mad.hi.u32 %0, %1, 256, 0x4B000000;" : "=r"(m) : "r"(x));
+      asm("mad.hi.u32 %0, %1, 256, %2;" : "=r"(m) : "r"(x), "n"(MAGIC));
 #else
-      m = __funnelshift_r(x, 0x004B0000u, 24);        // (x >> 24) | 0x4B000000
+      m = __funnelshift_r(x, MAGIC >> 8, 24);         // (x >> 24) | MAGIC
 #endif
     } else {
       uint32_t t;                                      // (x << (24 - 8b)) >> 24, both on the FMA pipe
       asm("mul.lo.u32 %0, %1, %2;" : "=r"(t) : "r"(x), "r"(1u << (24 - 8 * b)));
-      asm("mad.hi.u32 %0, %1, 256, 0x4B000000;" : "=r"(m) : "r"(t));
+      asm("mad.hi.u32 %0, %1, 256, %2;" : "=r"(m) : "r"(t), "n"(MAGIC));
     }
   } else if (b == 3) {
-    m = __funnelshift_r(x, 0x004B0000u, 24);
+    m = __funnelshift_r(x, MAGIC >> 8, 24);
   } else {
-    m = __byte_perm(x, 0x4B000000u, 0x7650u | (uint32_t)b);
+    m = __byte_perm(x, MAGIC, 0x7650u | (uint32_t)b);
   }
   return __uint_as_float(m);
 }
@@ -547,6 +570,47 @@ __device__ __forceinline__ int unbias(float t) {
 #endif
 }
 
+// Signed variant for the chroma rows of the reference's matrix (watermarking.py:37-39): the
+// bit pattern of the float 1.5*2^23 + (cr*r + cg*g + cb*b) for pixel j, |sum| < 2^22.
+__device__ __forceinline__ uint32_t dp2a_lo_s(uint32_t bytes, uint32_t w16x2, uint32_t acc) {
+  int32_t d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"((int32_t)w16x2), "r"(bytes), "r"((int32_t)acc));
+  return (uint32_t)d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi_s(uint32_t bytes, uint32_t w16x2, uint32_t acc) {
+  int32_t d;
+  asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"((int32_t)w16x2), "r"(bytes), "r"((int32_t)acc));
+  return (uint32_t)d;
+}
+template <int CR, int CG, int CB>
+__device__ __forceinline__ float pixel_dot_magic_s(const uint32_t (&w)[6], int j) {
+  constexpr uint32_t r = (uint32_t)(uint16_t)(int16_t)CR, g = (uint32_t)(uint16_t)(int16_t)CG,
+                     b = (uint32_t)(uint16_t)(int16_t)CB;
+  constexpr uint32_t kRG = r | (g << 16), kB_ = b, k_R = r << 16, kGB = g | (b << 16);
+  const int k = (3 * j) >> 2;
+  uint32_t m;
+  switch ((3 * j) & 3) {
+    case 0: m = dp2a_hi_s(w[k], kB_, dp2a_lo_s(w[k], kRG, 0x4B400000u)); break;
+    case 1: m = dp2a_hi_s(w[k], kGB, dp2a_lo_s(w[k], k_R, 0x4B400000u)); break;
+    case 2: m = dp2a_lo_s(w[k + 1], kB_, dp2a_hi_s(w[k], kRG, 0x4B400000u)); break;
+    default: m = dp2a_lo_s(w[k + 1], kGB, dp2a_hi_s(w[k], k_R, 0x4B400000u)); break;
+  }
+  return __uint_as_float(m);
+}
+// Pixel pairs of a row whose pass 2 goes through exact integer chroma (4 IDP.2A per pixel on
+// the FMA pipe, 5 packed FMAs per pair) instead of byte extraction (3 PRMT per pixel on the
+// ALU pipe, 9 packed FMAs per pair): 0..4, a pipe-balance knob.  Needs the luma stash in
+// 1/1000 units (TMF_LUMA_IDP).
+#ifndef TMF_PASS2_IDP_PAIRS
+#define TMF_PASS2_IDP_PAIRS 0   // measured slower for every value 1..4 (profiles/r01_sweep_variants.txt, table 9)
+#endif
+#ifndef TMF_PASS2_DELTA
+#define TMF_PASS2_DELTA 1       // pass 2 as k_c + small term (see embed_row_fast2)
+#endif
+#if TMF_PASS2_IDP_PAIRS > 0 && !TMF_LUMA_IDP
+#error "TMF_PASS2_IDP_PAIRS needs TMF_LUMA_IDP"
+#endif
+
 // pass 2 for one row, packed: bytes of the row, its luma (4 pairs), w (4 pairs), f, c ->
 // six output words.  Same arithmetic as tmf::embed_row_fast + pack4_sat_u8.
 __device__ __forceinline__ void embed_row_fast2(const uint32_t (&w)[6], const float2 (&y2)[4], const float2 (&w2)[4],
@@ -561,13 +625,43 @@ __device__ __forceinline__ void embed_row_fast2(const uint32_t (&w)[6], const fl
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     const int B = 6 * p;
-    const float2 r2 = bytes_to_float2(w, B), g2 = bytes_to_float2(w, B + 1), b2 = bytes_to_float2(w, B + 2);
     const float2 d2 = __fmul2_rn(bc2(du), w2[p]);
-    const float2 R = __ffma2_rn(bc2(1.0005f), r2, __ffma2_rn(bc2(-8.57e-4f), g2, __ffma2_rn(bc2(3.57e-4f), b2, d2)));
-    const float2 G = __ffma2_rn(bc2(1.36e-4f), r2, __ffma2_rn(bc2(1.00003f), g2, __ffma2_rn(bc2(-1.66e-4f), b2, d2)));
-    const float2 Bv = __ffma2_rn(bc2(-6.37e-4f), r2, __ffma2_rn(bc2(1.37e-4f), g2, __ffma2_rn(bc2(1.0005f), b2, d2)));
-    const float2 tR = __fadd2_rd(R, bc2(12582912.0f)), tG = __fadd2_rd(G, bc2(12582912.0f)),
-                 tB = __fadd2_rd(Bv, bc2(12582912.0f));
+    float2 tR, tG, tB;
+    if (p < TMF_PASS2_IDP_PAIRS) {
+      // y' = y + d in 0..255 units from the stash (1000 * y255, exact); 1000 * chroma exact
+      const float2 yd = __ffma2_rn(bc2(1.0e-3f), y2[p], d2);
+      const float2 cb = __fadd2_rn(make_float2(pixel_dot_magic_s<-169, -331, 500>(w, 2 * p),
+                                               pixel_dot_magic_s<-169, -331, 500>(w, 2 * p + 1)), bc2(-12582912.0f));
+      const float2 cr = __fadd2_rn(make_float2(pixel_dot_magic_s<500, -419, -81>(w, 2 * p),
+                                               pixel_dot_magic_s<500, -419, -81>(w, 2 * p + 1)), bc2(-12582912.0f));
+      const float2 R = __ffma2_rn(bc2(1.403e-3f), cr, yd);                      // watermarking.py:61-67
+      const float2 G = __ffma2_rn(bc2(-0.344e-3f), cb, __ffma2_rn(bc2(-0.714e-3f), cr, yd));
+      const float2 Bv = __ffma2_rn(bc2(1.773e-3f), cb, yd);
+      tR = __fadd2_rd(R, bc2(12582912.0f)); tG = __fadd2_rd(G, bc2(12582912.0f)); tB = __fadd2_rd(Bv, bc2(12582912.0f));
+    } else {
+#if TMF_PASS2_DELTA
+      // M = I + E with E's rows summing to zero (a grey pixel maps to itself), so
+      //   out_c = floor(k_c + s_c),  s_c = E_c0 (r - g) + E_c2 (b - g) + d   (|s_c| small).
+      // The bytes are extracted straight onto the quantiser's bias, m_c = 1.5*2^23 + k_c
+      // (exact); r - g and b - g are exact differences of those; and FADD.RD(s_c, m_c) is
+      // 1.5*2^23 + floor(k_c + s_c) exactly.  Two FMAs per sample instead of three, no
+      // separate removal of the bias, and the small term s_c is carried at full precision.
+      const float2 mr = make_float2(byte_to_magic<0x4B400000u>(w, B), byte_to_magic<0x4B400000u>(w, B + 3));
+      const float2 mg = make_float2(byte_to_magic<0x4B400000u>(w, B + 1), byte_to_magic<0x4B400000u>(w, B + 4));
+      const float2 mb = make_float2(byte_to_magic<0x4B400000u>(w, B + 2), byte_to_magic<0x4B400000u>(w, B + 5));
+      const float2 u = __ffma2_rn(mg, bc2(-1.0f), mr), v = __ffma2_rn(mg, bc2(-1.0f), mb);
+      const float2 sR = __ffma2_rn(bc2(5.00e-4f), u, __ffma2_rn(bc2(3.57e-4f), v, d2));
+      const float2 sG = __ffma2_rn(bc2(1.36e-4f), u, __ffma2_rn(bc2(-1.66e-4f), v, d2));
+      const float2 sB = __ffma2_rn(bc2(-6.37e-4f), u, __ffma2_rn(bc2(5.00e-4f), v, d2));
+      tR = __fadd2_rd(sR, mr); tG = __fadd2_rd(sG, mg); tB = __fadd2_rd(sB, mb);
+#else
+      const float2 r2 = bytes_to_float2(w, B), g2 = bytes_to_float2(w, B + 1), b2 = bytes_to_float2(w, B + 2);
+      const float2 R = __ffma2_rn(bc2(1.0005f), r2, __ffma2_rn(bc2(-8.57e-4f), g2, __ffma2_rn(bc2(3.57e-4f), b2, d2)));
+      const float2 G = __ffma2_rn(bc2(1.36e-4f), r2, __ffma2_rn(bc2(1.00003f), g2, __ffma2_rn(bc2(-1.66e-4f), b2, d2)));
+      const float2 Bv = __ffma2_rn(bc2(-6.37e-4f), r2, __ffma2_rn(bc2(1.37e-4f), g2, __ffma2_rn(bc2(1.0005f), b2, d2)));
+      tR = __fadd2_rd(R, bc2(12582912.0f)); tG = __fadd2_rd(G, bc2(12582912.0f)); tB = __fadd2_rd(Bv, bc2(12582912.0f));
+#endif
+    }
     q[B] = unbias(tR.x); q[B + 1] = unbias(tG.x); q[B + 2] = unbias(tB.x);
     q[B + 3] = unbias(tR.y); q[B + 4] = unbias(tG.y); q[B + 5] = unbias(tB.y);
   }
@@ -622,7 +716,8 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
 #if TMF_USE_F32X2
     uint32_t wd[6];
     load_row24<VEC>(src + (size_t)i * g.row_pitch, wd);
-    const float2 y2[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb.x, yb.y), make_float2(yb.z, yb.w)};
+    float2 y2[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb.x, yb.y), make_float2(yb.z, yb.w)};
+    if (TMF_PASS2_IDP_PAIRS > 0 && mark == 0) row_luma2(wd, y2);   // no stash: pass 1 was skipped
     embed_row_fast2(wd, y2, w2, f, c, o);
 #else
     float r[8], gg[8], b[8];
@@ -1008,6 +1103,10 @@ int make_geom(int n, int h, int w, size_t img_stride, int block, BlockGeom& g) {
   g.h = h; g.w = w; g.bs = block; g.nbh = h / block; g.nbw = w / block;
   g.blocks_per_img = (long long)g.nbh * g.nbw;
   g.total_blocks = g.blocks_per_img * n;
+  if (g.total_blocks > 0x7fffffffLL)   // 2^31 blocks of 192 B would be 412 GB of pixels
+    return fail(TMF_ERR_BAD_ARG, "batch too large: %lld blocks (limit 2^31 - 1 per call)", g.total_blocks);
+  g.div_bpi = make_fastdiv((uint32_t)(g.blocks_per_img > 0 ? g.blocks_per_img : 1));
+  g.div_nbw = make_fastdiv((uint32_t)(g.nbw > 0 ? g.nbw : 1));
   g.img_stride = img_stride;
   g.row_pitch = (size_t)w * 3;
   return TMF_OK;

@@ -16,22 +16,13 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
 VARIANTS = {
     "base": {},
-    "mask0": {"TMF_EXTRACT_IMAD_MASK": 0},
-    "maskC": {"TMF_EXTRACT_IMAD_MASK": 0xC},
-    "quant1": {"TMF_QUANT_IMAD": 1},
-    "quant2": {"TMF_QUANT_IMAD": 2},
-    "ctas5": {"TMF_EMBED_MIN_CTAS": 5, "TMF_FAST_MIN_CTAS": 5},
-    "ctas7x": {"TMF_FAST_MIN_CTAS": 7},
-    "ctas8x": {"TMF_FAST_MIN_CTAS": 8},
-    "unroll2": {"TMF_ROW_UNROLL": 2},
-    "unroll8": {"TMF_ROW_UNROLL": 8},
-    "noidp": {"TMF_LUMA_IDP": 0},
-    "p2idp1": {"TMF_PASS2_IDP_PAIRS": 1},
-    "p2idp2": {"TMF_PASS2_IDP_PAIRS": 2},
-    "p2idp3": {"TMF_PASS2_IDP_PAIRS": 3},
-    "p2idp4": {"TMF_PASS2_IDP_PAIRS": 4},
-    "p2idp4_mask0": {"TMF_PASS2_IDP_PAIRS": 4, "TMF_EXTRACT_IMAD_MASK": 0},
-    "p2idp2_mask0": {"TMF_PASS2_IDP_PAIRS": 2, "TMF_EXTRACT_IMAD_MASK": 0},
+    "stash0": {"TMF_STASH": 0},
+    "stash0_c7": {"TMF_STASH": 0, "TMF_EMBED_MIN_CTAS": 7},
+    "stash0_c8": {"TMF_STASH": 0, "TMF_EMBED_MIN_CTAS": 8},
+    "stash0_u2": {"TMF_STASH": 0, "TMF_ROW_UNROLL": 2},
+    "stash2": {"TMF_STASH": 2},
+    "stash2_c7": {"TMF_STASH": 2, "TMF_EMBED_MIN_CTAS": 7},
+    "stash2_c8": {"TMF_STASH": 2, "TMF_EMBED_MIN_CTAS": 8},
 }
 
 

@@ -16,13 +16,9 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
 VARIANTS = {
     "base": {},
-    "stash0": {"TMF_STASH": 0},
-    "stash0_c7": {"TMF_STASH": 0, "TMF_EMBED_MIN_CTAS": 7},
-    "stash0_c8": {"TMF_STASH": 0, "TMF_EMBED_MIN_CTAS": 8},
-    "stash0_u2": {"TMF_STASH": 0, "TMF_ROW_UNROLL": 2},
-    "stash2": {"TMF_STASH": 2},
-    "stash2_c7": {"TMF_STASH": 2, "TMF_EMBED_MIN_CTAS": 7},
-    "stash2_c8": {"TMF_STASH": 2, "TMF_EMBED_MIN_CTAS": 8},
+    "biasq": {"TMF_QUANT_DENORM": 0},
+    "c7": {"TMF_EMBED_MIN_CTAS": 7},
+    "u2": {"TMF_ROW_UNROLL": 2},
 }
 
 
@@ -42,7 +38,7 @@ def build():
             regs = []
             lines = o.splitlines()
             for i, l in enumerate(lines):
-                if "Compiling entry function" in l and ("embed_fastILi8" in l or "extract_fastILi8" in l):
+                if "Compiling entry function" in l and ("embed_fastILi8" in l or "extract_fastILi8" in l or "_tma" in l):
                     regs.append(" ".join(x.strip() for x in lines[i + 2:i + 4]))
             print(name, "ok" if p.returncode == 0 else "FAILED\n" + o[-2000:], "|", " || ".join(regs))
 

@@ -18,7 +18,9 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <type_traits>
 
 #include "../../include/tmf_wm.h"
@@ -66,7 +68,11 @@ constexpr int kRowUnroll = TMF_ROW_UNROLL;
 // ---------------------------------------------------------------------------
 template <int VEC>
 __device__ __forceinline__ void load_row24(const uint8_t* __restrict__ p, uint32_t (&w)[6]) {
-  if (VEC == 8) {
+  if (VEC == 0) {               // a row staged in shared memory (TMA tile): three LDS.64
+    const uint2* q = reinterpret_cast<const uint2*>(p);
+    uint2 a = q[0], b = q[1], c = q[2];
+    w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y; w[4] = c.x; w[5] = c.y;
+  } else if (VEC == 8) {
     const uint2* q = reinterpret_cast<const uint2*>(p);
     uint2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
     w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y; w[4] = c.x; w[5] = c.y;
@@ -85,7 +91,7 @@ __device__ __forceinline__ void load_row24(const uint8_t* __restrict__ p, uint32
 
 template <int VEC>
 __device__ __forceinline__ void store_row24(uint8_t* __restrict__ p, const uint32_t (&w)[6]) {
-  if (VEC == 8) {
+  if (VEC == 8 || VEC == 0) {
     uint2* q = reinterpret_cast<uint2*>(p);
     q[0] = make_uint2(w[0], w[1]); q[1] = make_uint2(w[2], w[3]); q[2] = make_uint2(w[4], w[5]);
   } else if (VEC == 4) {
@@ -607,6 +613,12 @@ __device__ __forceinline__ float pixel_dot_magic_s(const uint32_t (&w)[6], int j
 #ifndef TMF_PASS2_DELTA
 #define TMF_PASS2_DELTA 1       // pass 2 as k_c + small term (see embed_row_fast2)
 #endif
+#ifndef TMF_QUANT_DENORM
+#define TMF_QUANT_DENORM 1      // the quantiser floors straight onto the integer level (subnormal trick, embed_row_fast2)
+#endif
+#if TMF_QUANT_DENORM && TMF_PASS2_IDP_PAIRS > 0
+#error "TMF_QUANT_DENORM scales du by 2^-49: not combined with the TMF_PASS2_IDP_PAIRS experiment"
+#endif
 #if TMF_PASS2_IDP_PAIRS > 0 && !TMF_LUMA_IDP
 #error "TMF_PASS2_IDP_PAIRS needs TMF_LUMA_IDP"
 #endif
@@ -620,7 +632,8 @@ __device__ __forceinline__ void embed_row_fast2(const uint32_t (&w)[6], const fl
   for (int p = 1; p < 4; ++p) acc = __ffma2_rn(y2[p], w2[p], acc);
   // tmf::dot8 accumulates sequentially; the pairwise order differs by rounding only in z,
   // which is scaled by f ~ 1e-3: far below the quantiser's resolution
-  const float du = fmaf(f, acc.x + acc.y, c);
+  float du = fmaf(f, acc.x + acc.y, c);
+  if (TMF_PASS2_DELTA && TMF_QUANT_DENORM) du *= 1.7763568394002505e-15f;   // 2^-49, see below (exact scaling)
   int q[24];
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
@@ -639,7 +652,27 @@ __device__ __forceinline__ void embed_row_fast2(const uint32_t (&w)[6], const fl
       const float2 Bv = __ffma2_rn(bc2(1.773e-3f), cb, yd);
       tR = __fadd2_rd(R, bc2(12582912.0f)); tG = __fadd2_rd(G, bc2(12582912.0f)); tB = __fadd2_rd(Bv, bc2(12582912.0f));
     } else {
-#if TMF_PASS2_DELTA
+#if TMF_PASS2_DELTA && TMF_QUANT_DENORM
+      // As below (out_c = floor(k_c + s_c)), but the floor lands DIRECTLY on the integer level:
+      // byte k extracted with a zero filler IS the bit pattern of the subnormal float k * 2^-149,
+      // and FFMA.RM(s_c * 2^-49, 2^-100, k * 2^-149) is the exact sum (k_c + s_c) * 2^-149 rounded
+      // toward -inf to a multiple of 2^-149, i.e. the float whose bits are floor(k_c + s_c) - or
+      // a negative float (sign bit set = a hugely negative s32) when the level is below 0,
+      // which the saturating pack clips to 0 like any other negative.  No bias to remove: 24
+      // integer subtractions per row gone.  The 2^-49 rides in E's constants (scaled by 2^100:
+      // the differences u, v are subnormal too, (r - g) * 2^-149, exact) and in du (caller);
+      // power-of-two scalings are exact, so every value is the one the biased form computes.
+      const float2 mr = make_float2(byte_to_magic<0u>(w, B), byte_to_magic<0u>(w, B + 3));
+      const float2 mg = make_float2(byte_to_magic<0u>(w, B + 1), byte_to_magic<0u>(w, B + 4));
+      const float2 mb = make_float2(byte_to_magic<0u>(w, B + 2), byte_to_magic<0u>(w, B + 5));
+      const float2 u = __ffma2_rn(mg, bc2(-1.0f), mr), v = __ffma2_rn(mg, bc2(-1.0f), mb);
+      constexpr float k2p100 = 1.2676506002282294e30f;      // 2^100
+      const float2 sR = __ffma2_rn(bc2(5.00e-4f * k2p100), u, __ffma2_rn(bc2(3.57e-4f * k2p100), v, d2));
+      const float2 sG = __ffma2_rn(bc2(1.36e-4f * k2p100), u, __ffma2_rn(bc2(-1.66e-4f * k2p100), v, d2));
+      const float2 sB = __ffma2_rn(bc2(-6.37e-4f * k2p100), u, __ffma2_rn(bc2(5.00e-4f * k2p100), v, d2));
+      constexpr float k2m100 = 7.888609052210118e-31f;      // 2^-100
+      tR = __ffma2_rd(sR, bc2(k2m100), mr); tG = __ffma2_rd(sG, bc2(k2m100), mg); tB = __ffma2_rd(sB, bc2(k2m100), mb);
+#elif TMF_PASS2_DELTA
       // M = I + E with E's rows summing to zero (a grey pixel maps to itself), so
       //   out_c = floor(k_c + s_c),  s_c = E_c0 (r - g) + E_c2 (b - g) + d   (|s_c| small).
       // The bytes are extracted straight onto the quantiser's bias, m_c = 1.5*2^23 + k_c
@@ -662,8 +695,13 @@ __device__ __forceinline__ void embed_row_fast2(const uint32_t (&w)[6], const fl
       tR = __fadd2_rd(R, bc2(12582912.0f)); tG = __fadd2_rd(G, bc2(12582912.0f)); tB = __fadd2_rd(Bv, bc2(12582912.0f));
 #endif
     }
-    q[B] = unbias(tR.x); q[B + 1] = unbias(tG.x); q[B + 2] = unbias(tB.x);
-    q[B + 3] = unbias(tR.y); q[B + 4] = unbias(tG.y); q[B + 5] = unbias(tB.y);
+    if (TMF_PASS2_DELTA && TMF_QUANT_DENORM && p >= TMF_PASS2_IDP_PAIRS) {
+      q[B] = __float_as_int(tR.x); q[B + 1] = __float_as_int(tG.x); q[B + 2] = __float_as_int(tB.x);
+      q[B + 3] = __float_as_int(tR.y); q[B + 4] = __float_as_int(tG.y); q[B + 5] = __float_as_int(tB.y);
+    } else {
+      q[B] = unbias(tR.x); q[B + 1] = unbias(tG.x); q[B + 2] = unbias(tB.x);
+      q[B + 3] = unbias(tR.y); q[B + 4] = unbias(tG.y); q[B + 5] = unbias(tB.y);
+    }
   }
 #pragma unroll
   for (int k = 0; k < 6; ++k) o[k] = tmf::pack4_sat_u8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
@@ -729,6 +767,139 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
     for (int k = 0; k < 6; ++k) o[k] = tmf::pack4_sat_u8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
 #endif
     store_row24<VEC>(dst + (size_t)i * g.row_pitch, o);
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// Fused embed, FAST mode, rows staged through shared memory by the TMA engine.
+//
+// Why: with per-thread row accesses (k_embed_fast) a warp's 64-bit load covers 256 useful
+// bytes spread over 768, i.e. 6-7 L1 wavefronts instead of 2, three times per row; the six
+// resident CTAs own 144 KB of input rows but share < 64 KB of L1, so pass 2 re-reads most
+// rows from L2 (ncu: L1 hit rate 56 %, 20 % of warp samples on long_scoreboard, L1 wavefronts
+// 46 % busy), and every 32-byte output sector reaches L2 in three partial writes.  Here a
+// WARP owns 32 adjacent blocks = 8 image-row pieces of 768 contiguous bytes:
+//   * lanes 0-7 ask the TMA engine for one row piece each (cp.async.bulk global -> shared,
+//     one mbarrier per warp; a warp that straddles the end of a block-row has two runs, the
+//     second issued by lanes 8-15) - one warp instruction, not a loop in one lane,
+//   * both row passes read the tile with conflict-free LDS.64 (thread stride 24 B: the 16
+//     lanes of a half-warp hit 16 distinct bank pairs),
+//   * pass 2 writes its bytes back IN PLACE (the 24 bytes of a row piece are private to
+//     their lane), and the same lanes hand the tile to the TMA engine again
+//     (cp.async.bulk shared -> global): full-line writes, no per-thread STG,
+//   * nothing else is parked in shared memory: pass 2 recomputes the row's exact integer luma
+//     from the staged bytes (8 IDP.2A) - the same values pass 1 had, so the results are
+//     identical to k_embed_fast's - which keeps the footprint at 24 KB per CTA, 6 CTAs/SM.
+// No __syncthreads: warps of a CTA run independently.  Needs 16-byte aligned runs: base
+// pointers, image stride and 3*W multiples of 16, an even number (>= 32) of blocks per
+// block-row; everything else takes k_embed_fast.
+// ---------------------------------------------------------------------------
+#ifndef TMF_TMA_MIN_CTAS
+#define TMF_TMA_MIN_CTAS 6
+#endif
+constexpr int kTileRowBytes = 32 * 24;             // one image-row piece of a warp's 32 blocks
+constexpr int kTileBytes = 8 * kTileRowBytes;      // 6 KB per warp
+constexpr int kWarps = kThreads / 32;
+constexpr int kEmbedTmaSmem = kWarps * kTileBytes + kWarps * 8;   // tiles + one mbarrier per warp
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "TMF_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra TMF_WAIT_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+// A warp's 32 consecutive blocks are one run, or two when they straddle the end of a
+// block-row (nbw >= 32).  Lane L < 16 moves image row (L & 7) of run (L >> 3).
+struct WarpRuns {
+  size_t org;        // byte offset (in the batch) of this lane's run
+  uint32_t soff;     // byte offset of the run inside a tile row
+  uint32_t bytes;    // 0: this lane moves nothing
+};
+__device__ __forceinline__ WarpRuns warp_runs(const BlockGeom& g, int lane, int cnt, size_t my_org, int my_bx) {
+  const int bx0 = __shfl_sync(0xffffffffu, my_bx, 0);
+  int run0 = g.nbw - bx0;
+  if (run0 > cnt) run0 = cnt;
+  const size_t org0 = __shfl_sync(0xffffffffu, (unsigned long long)my_org, 0);
+  const size_t org1 = __shfl_sync(0xffffffffu, (unsigned long long)my_org, run0 & 31);   // first block of run 1
+  WarpRuns r;
+  const int which = lane >> 3;
+  r.org = which == 0 ? org0 : org1;
+  r.soff = which == 0 ? 0u : (uint32_t)run0 * 24u;
+  r.bytes = which == 0 ? (uint32_t)run0 * 24u : (which == 1 ? (uint32_t)(cnt - run0) * 24u : 0u);
+  return r;
+}
+
+__global__ void __launch_bounds__(kThreads, TMF_TMA_MIN_CTAS)
+k_embed_fast_tma(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGeom g,
+                 const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long gw0 = (long long)blockIdx.x * kThreads + warp * 32;   // first block of this warp
+  if (gw0 >= g.total_blocks) return;                                    // whole warp; nothing is CTA-wide here
+  const long long rem = g.total_blocks - gw0;
+  const int cnt = rem < 32 ? (int)rem : 32;
+  const bool live = lane < cnt;
+  uint8_t* tile = smem + warp * kTileBytes;
+  const uint32_t tile_s = smem_u32(tile);
+  const uint32_t bar = smem_u32(smem + kWarps * kTileBytes + warp * 8);
+  if (lane == 0) mbar_init(bar, 1);
+  long long img; int by, bx;
+  const size_t org = block_origin(g, gw0 + (live ? lane : 0), img, by, bx);
+  const WarpRuns mv = warp_runs(g, lane, cnt, org, bx);
+  const int row = lane & 7;
+  __syncwarp();                      // the barrier is initialised before anything signals or polls it
+  if (lane == 0) mbar_expect_tx(bar, (uint32_t)cnt * 24u * 8u);
+  if (mv.bytes) bulk_g2s(tile_s + row * kTileRowBytes + mv.soff, rgb + mv.org + (size_t)row * g.row_pitch, mv.bytes, bar);
+  uint32_t mark = 0;
+  if (live) mark = (uint32_t)__ldg(wm + (wm_shared ? 0 : img * g.blocks_per_img) + (long long)by * g.nbw + bx);
+  mbar_wait(bar, 0);
+  uint8_t* mine = tile + lane * 24;
+  float w[8], f = 0.0f, c = 0.0f;
+  if (live && mark != 0) {
+    float gm[36];
+    gram_of_block<0, false>(mine, kTileRowBytes, gm);
+    tmf::embed_block_scalars_fast(gm, alpha, mark, w, f, c, nullptr, TMF_LUMA_UNIT);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = 0.0f;
+  }
+  if (live) {
+    const float2 w2[4] = {make_float2(w[0], w[1]), make_float2(w[2], w[3]), make_float2(w[4], w[5]), make_float2(w[6], w[7])};
+#pragma unroll kRowUnroll
+    for (int i = 0; i < 8; ++i) {
+      uint32_t o[6], wd[6];
+      load_row24<0>(mine + i * kTileRowBytes, wd);
+      float2 y2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      if (mark != 0 || TMF_PASS2_IDP_PAIRS > 0) row_luma2(wd, y2);
+      embed_row_fast2(wd, y2, w2, f, c, o);
+      store_row24<0>(mine + i * kTileRowBytes, o);
+    }
+  }
+  // generic-proxy writes -> visible to the async proxy, then the moving lanes hand the tile over
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (mv.bytes) {
+    bulk_s2g(out + mv.org + (size_t)row * g.row_pitch, tile_s + row * kTileRowBytes + mv.soff, mv.bytes);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tile must outlive the reads
   }
 }
 
@@ -1119,6 +1290,33 @@ int pick_vec(const BlockGeom& g, const void* p0, const void* p1, const void* p2 
   return 1;
 }
 
+// The TMA-staged embed kernel (k_embed_fast_tma) is an opt-in alternative: measured 4-5 % slower
+// than the per-thread kernel on 1080p batches (it issues better, 72 % vs 66 %
+// of the slots, but executes 14 % more instructions), so it runs only when TMF_EMBED_TMA=1 is in
+// the environment (read once) - for A/B measurements and for testing the two code paths against
+// each other (identical outputs).  It needs 16-byte aligned runs and >= 32 blocks per block-row.
+bool tma_ok(const BlockGeom& g, const void* p0, const void* p1, const void* p2 = nullptr) {
+  static const bool enabled = [] { const char* e = getenv("TMF_EMBED_TMA"); return e && e[0] == '1'; }();
+  if (!enabled) return false;
+  uintptr_t bits = (uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2 | (uintptr_t)g.img_stride | (uintptr_t)g.row_pitch;
+  return (bits & 15) == 0 && (g.nbw & 1) == 0 && g.nbw >= 32 && g.bs == 8;
+}
+
+// opt in to > 48 KB of dynamic shared memory, once per device (idempotent, thread-safe)
+int tma_kernel_attrs() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(TMF_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+  static std::atomic<unsigned long long> done{0};
+  if (dev < 64 && (done.load(std::memory_order_acquire) >> dev) & 1ull) return TMF_OK;
+  e = cudaFuncSetAttribute(k_embed_fast_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmbedTmaSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_embed_fast_tma, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(TMF_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+  if (dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+  return TMF_OK;
+}
+
 unsigned grid_for(long long items, int per_cta) { return (unsigned)((items + per_cta - 1) / per_cta); }
 
 
@@ -1188,7 +1386,10 @@ int tmf_embed_rgb8(const uint8_t* rgb, uint8_t* out, int n, int h, int w, size_t
   } else if (g.total_blocks > 0) {
     const unsigned grid = grid_for(g.total_blocks, kThreads);
     const int vec = pick_vec(g, rgb, out);
-    if (mode == TMF_MODE_FAST) {
+    if (mode == TMF_MODE_FAST && tma_ok(g, rgb, out)) {
+      if (int rc = tma_kernel_attrs()) return rc;
+      k_embed_fast_tma<<<grid, kThreads, kEmbedTmaSmem, st>>>(rgb, out, g, wm, wm_shared, alpha);
+    } else if (mode == TMF_MODE_FAST) {
       switch (vec) {
         case 8: k_embed_fast<8><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
         case 4: k_embed_fast<4><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;

@@ -16,9 +16,9 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
 VARIANTS = {
     "base": {},
-    "biasq": {"TMF_QUANT_DENORM": 0},
-    "c7": {"TMF_EMBED_MIN_CTAS": 7},
-    "u2": {"TMF_ROW_UNROLL": 2},
+    "maxmore5": {"TMF_FAST_MAX_MORE": 5},
+    "maxmore8": {"TMF_FAST_MAX_MORE": 8},
+    "slack2": {"TMF_FAST_FROB_SLACK": "2.0e-6f"},
 }
 
 

@@ -119,6 +119,37 @@ TMF_HD float dot8(const float* a, const float* b) { return dotn<8>(a, b); }
 #define TMF_FAST_TOL_VEC_EXTRACT 3.0e-4f   // sigma0 only: second order in the vector error
 #define TMF_FAST_MAX_LEVELS 18
 
+// ||m||_F^2 = tr(m^2) for symmetric m (upper triangle)
+template <int N = 8>
+TMF_HD float sym_frob2(const float* m) {
+  float d = 0.f, o = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    d = fmaf(m[sym_idx<N>(i, i)], m[sym_idx<N>(i, i)], d);
+#pragma unroll
+    for (int j = i + 1; j < N; ++j) o = fmaf(m[sym_idx<N>(i, j)], m[sym_idx<N>(i, j)], o);
+  }
+  return fmaf(2.0f, o, d);
+}
+
+// Second certificate, used only when the trace bound is too weak (textured / noise blocks,
+// where the trace bound charges mu_0 with ALL the other eigenvalues):
+//     mu_1^2 <= sum_{i>=1} mu_i^2 = tr(M^2) - mu_0^2 <= tr(M^2) - mu^^2     (mu^ <= mu_0)
+// so mu_1/mu_0 <= sqrt(tr(M^2) - mu^^2) / mu^.  For a noise block with seven comparable small
+// eigenvalues this is ~sqrt(7) times their ratio instead of 7 times it, which certifies a
+// handful of plain products (64 FMAs each) where the trace bound forced a squaring (~330).
+// The difference cancels when M is nearly rank one (both terms ~1, fp32 noise ~1e-6) - but
+// then the trace bound has already certified the block on the fast path: this branch runs only
+// when sum_{i>=1} mu_i / mu_0 is large (> ~0.06 for embed), hence tr(M^2) - mu_0^2 >= ~4e-4, and
+// the slack of 8e-6 (the worst-case fp32 rounding of a 64-term sum near 1, two orders below the
+// quantity) keeps the bound an upper bound.
+#ifndef TMF_FAST_FROB_SLACK
+#define TMF_FAST_FROB_SLACK 8.0e-6f
+#endif
+#ifndef TMF_FAST_MAX_MORE
+#define TMF_FAST_MAX_MORE 6                // plain products allowed after the first two, per level
+#endif
+
 template <bool EMBED, int N = 8>
 TMF_HD int top_pair(float* m, float* w, float& ww, float& mu) {
   constexpr int NS = N * (N + 1) / 2;
@@ -138,23 +169,34 @@ TMF_HD int top_pair(float* m, float* w, float& ww, float& mu) {
     const float xx = dotn<N>(x, x);
     xy = dotn<N>(x, y);
     yy = dotn<N>(y, y);
-    const float rho = fmaxf(xx - xy, 0.0f) * f_rcp_fast(xy);
+    float rho = fmaxf(xx - xy, 0.0f) * f_rcp_fast(xy);
     float err = theta * rho * rho;       // bound on tan(angle(y, v0))
     int more = 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       if (err > tol) { err *= rho; ++more; }
     }
+    if (err > tol && level < TMF_FAST_MAX_LEVELS - 1) {
+      const float t2 = sym_frob2<N>(m);  // tr(M^2)
+      const float muh = xy * f_rcp_fast(xx);                       // Rayleigh quotient of x, <= mu_0
+      const float r2 = fminf(rho, f_sqrt(fmaxf(t2 - muh * muh, 0.0f) + TMF_FAST_FROB_SLACK) * f_rcp_fast(muh));
+      float e2 = theta * r2 * r2;
+      int m2 = 0;
+#pragma unroll 1
+      for (int k = 0; k < TMF_FAST_MAX_MORE; ++k) {
+        if (e2 > tol) { e2 *= r2; ++m2; }
+      }
+      rho = r2;
+      if (e2 <= tol) { err = e2; more = m2; }
+    }
     if (err <= tol || level >= TMF_FAST_MAX_LEVELS - 1) {
+#pragma unroll 1
+      for (int k = 0; k < more; ++k) {   // rolled: one copy of the product (the predicated unrolled forms measured slower)
+        sym_matvec<N>(m, y, x);          // x = M y
+        xy = dotn<N>(y, x);              // w_{J-1}.w_J
+        yy = dotn<N>(x, x);              // w_J.w_J
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (k < more) {
-          sym_matvec<N>(m, y, x);        // x = M y
-          xy = dotn<N>(y, x);            // w_{J-1}.w_J
-          yy = dotn<N>(x, x);            // w_J.w_J
-#pragma unroll
-          for (int i = 0; i < N; ++i) y[i] = x[i];
-        }
+        for (int i = 0; i < N; ++i) y[i] = x[i];
       }
       products += more;
       break;

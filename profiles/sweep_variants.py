@@ -15,10 +15,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
 VARIANTS = {
-    "base": {},
-    "maxmore5": {"TMF_FAST_MAX_MORE": 5},
-    "maxmore8": {"TMF_FAST_MAX_MORE": 8},
-    "slack2": {"TMF_FAST_FROB_SLACK": "2.0e-6f"},
+    "c5": {"TMF_EMBED_MIN_CTAS": 5},
+    "c4": {"TMF_EMBED_MIN_CTAS": 4},
+    "c3": {"TMF_EMBED_MIN_CTAS": 3},
+    "c4_u8": {"TMF_EMBED_MIN_CTAS": 4, "TMF_ROW_UNROLL": 8},
+    "c5_u8": {"TMF_EMBED_MIN_CTAS": 5, "TMF_ROW_UNROLL": 8},
+    "x5": {"TMF_FAST_MIN_CTAS": 5},
+    "x4": {"TMF_FAST_MIN_CTAS": 4},
 }
 
 

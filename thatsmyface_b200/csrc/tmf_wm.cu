@@ -59,7 +59,11 @@ constexpr int kThreads = 128;
 #define TMF_FAST_MIN_CTAS 6   // __launch_bounds__ minimum CTAs/SM of the fast extract / sigma0 kernels
 #endif
 #ifndef TMF_EMBED_MIN_CTAS
-#define TMF_EMBED_MIN_CTAS 6  // ... of the fast embed kernel (profiles/r01_sweep_variants.txt, tables 4-5)
+#define TMF_EMBED_MIN_CTAS 5  // ... of the fast embed kernel: 5 since the subnormal quantiser (96 registers, 160 KB of stash
+                              // leave the L1 60 KB for the pass-2 re-reads; profiles/r01_sweep_variants.txt, tables 4-5, 14)
+#endif
+#ifndef TMF_EMBED_STASH
+#define TMF_EMBED_STASH 1     // 1: pass 1 parks the luma in shared memory for pass 2; 0: pass 2 recomputes it
 #endif
 constexpr int kRowUnroll = TMF_ROW_UNROLL;
 
@@ -725,8 +729,12 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
   long long img; int by, bx;
   const size_t org = block_origin(g, gb, img, by, bx);
   const uint8_t* src = rgb + org;
+#if TMF_EMBED_STASH
   __shared__ float4 lum[16 * kThreads];      // 32 KB: the block's luma, thread-private column
   float4* col = lum + threadIdx.x;
+#else
+  float4* col = nullptr;                     // nothing parked: pass 2 recomputes the luma (8 IDP.2A per row)
+#endif
   prefetch_block_rows(src, g.row_pitch);
   if (TMF_BULK_AHEAD > 0 && VEC == 8 && threadIdx.x == 0)
     bulk_prefetch_tile(rgb, g, ((long long)blockIdx.x + TMF_BULK_AHEAD) * kThreads);
@@ -735,7 +743,7 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
   float w[8], f = 0.0f, c = 0.0f;
   if (mark != 0) {
     float gm[36];
-    gram_of_block<VEC, true>(src, g.row_pitch, gm, col);
+    gram_of_block<VEC, TMF_EMBED_STASH != 0>(src, g.row_pitch, gm, col);
     tmf::embed_block_scalars_fast(gm, alpha, mark, w, f, c, nullptr, TMF_LUMA_UNIT);
   } else {
 #pragma unroll
@@ -750,12 +758,12 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
   for (int i = 0; i < 8; ++i) {
     uint32_t o[6];
     float4 ya = make_float4(0.f, 0.f, 0.f, 0.f), yb = ya;
-    if (mark != 0) { ya = col[(2 * i) * kThreads]; yb = col[(2 * i + 1) * kThreads]; }
+    if (TMF_EMBED_STASH && mark != 0) { ya = col[(2 * i) * kThreads]; yb = col[(2 * i + 1) * kThreads]; }
 #if TMF_USE_F32X2
     uint32_t wd[6];
     load_row24<VEC>(src + (size_t)i * g.row_pitch, wd);
     float2 y2[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb.x, yb.y), make_float2(yb.z, yb.w)};
-    if (TMF_PASS2_IDP_PAIRS > 0 && mark == 0) row_luma2(wd, y2);   // no stash: pass 1 was skipped
+    if ((!TMF_EMBED_STASH && mark != 0) || (TMF_PASS2_IDP_PAIRS > 0 && mark == 0)) row_luma2(wd, y2);
     embed_row_fast2(wd, y2, w2, f, c, o);
 #else
     float r[8], gg[8], b[8];

@@ -15,13 +15,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
 VARIANTS = {
-    "c5": {"TMF_EMBED_MIN_CTAS": 5},
-    "c4": {"TMF_EMBED_MIN_CTAS": 4},
-    "c3": {"TMF_EMBED_MIN_CTAS": 3},
-    "c4_u8": {"TMF_EMBED_MIN_CTAS": 4, "TMF_ROW_UNROLL": 8},
-    "c5_u8": {"TMF_EMBED_MIN_CTAS": 5, "TMF_ROW_UNROLL": 8},
-    "x5": {"TMF_FAST_MIN_CTAS": 5},
-    "x4": {"TMF_FAST_MIN_CTAS": 4},
+    "base": {},
+    "rp1": {"TMF_EMBED_REPREFETCH": 1},
+    "rp2": {"TMF_EMBED_REPREFETCH": 2},
 }
 
 

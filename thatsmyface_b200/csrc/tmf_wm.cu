@@ -62,6 +62,9 @@ constexpr int kThreads = 128;
 #define TMF_EMBED_MIN_CTAS 5  // ... of the fast embed kernel: 5 since the subnormal quantiser (96 registers, 160 KB of stash
                               // leave the L1 60 KB for the pass-2 re-reads; profiles/r01_sweep_variants.txt, tables 4-5, 14)
 #endif
+#ifndef TMF_EMBED_REPREFETCH
+#define TMF_EMBED_REPREFETCH 0  // ask L1 for the block's rows again before (1) / after (2) the eigen-solve
+#endif
 #ifndef TMF_EMBED_STASH
 #define TMF_EMBED_STASH 1     // 1: pass 1 parks the luma in shared memory for pass 2; 0: pass 2 recomputes it
 #endif
@@ -744,7 +747,9 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
   if (mark != 0) {
     float gm[36];
     gram_of_block<VEC, TMF_EMBED_STASH != 0>(src, g.row_pitch, gm, col);
+    if (TMF_EMBED_REPREFETCH == 1) prefetch_block_rows(src, g.row_pitch);
     tmf::embed_block_scalars_fast(gm, alpha, mark, w, f, c, nullptr, TMF_LUMA_UNIT);
+    if (TMF_EMBED_REPREFETCH == 2) prefetch_block_rows(src, g.row_pitch);
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) w[i] = 0.0f;

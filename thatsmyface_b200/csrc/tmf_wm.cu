@@ -965,34 +965,44 @@ k_sigma0_fast(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, Block
 // ---------------------------------------------------------------------------
 template <int N>
 __device__ __forceinline__ size_t block_origin_n(const BlockGeom& g, long long gb, long long& img, int& by, int& bx) {
-  img = gb / g.blocks_per_img;
-  const int r = (int)(gb - img * g.blocks_per_img);
-  by = r / g.nbw;
-  bx = r - by * g.nbw;
-  return (size_t)img * g.img_stride + (size_t)by * N * g.row_pitch + (size_t)bx * (3 * N);
+  const uint32_t n = (uint32_t)gb;                       // total_blocks < 2^31 (make_geom): division-free, as block_origin
+  const uint32_t im = fastdiv(n, g.div_bpi);
+  const uint32_t r = n - im * (uint32_t)g.blocks_per_img;
+  const uint32_t y = fastdiv(r, g.div_nbw);
+  img = im;
+  by = (int)y;
+  bx = (int)(r - y * (uint32_t)g.nbw);
+  return (size_t)im * g.img_stride + (size_t)y * N * g.row_pitch + (size_t)bx * (3 * N);
+}
+
+// byte b (0..3) of w as a float, through the 2^23 magic number: one PRMT + one FADD on the
+// full-rate pipes instead of I2F.U8 (16/clk/SM, profiles/r01_ubench.txt)
+__device__ __forceinline__ float byte_of_word_f(uint32_t w, int b) {
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)b)) - 8388608.0f;
 }
 
 template <int N, int AL4>
 __device__ __forceinline__ void load_row_rgb255_n(const uint8_t* __restrict__ p, float* r, float* g, float* b) {
-  uint8_t raw[3 * N];
+  float v[3 * N];
   if (AL4 == 4) {
 #pragma unroll
     for (int k = 0; k < (3 * N) / 4; ++k) {
       const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p) + k);
-      raw[4 * k] = (uint8_t)w; raw[4 * k + 1] = (uint8_t)(w >> 8); raw[4 * k + 2] = (uint8_t)(w >> 16); raw[4 * k + 3] = (uint8_t)(w >> 24);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[4 * k + q] = byte_of_word_f(w, q);
     }
   } else if (AL4 == 2) {
 #pragma unroll
     for (int k = 0; k < (3 * N) / 2; ++k) {
-      const uint32_t w = __ldg(reinterpret_cast<const uint16_t*>(p) + k);
-      raw[2 * k] = (uint8_t)w; raw[2 * k + 1] = (uint8_t)(w >> 8);
+      const uint32_t w = __ldg(reinterpret_cast<const uint16_t*>(p) + k);     // I2F.U8 with a byte selector: measured
+      v[2 * k] = (float)(uint8_t)w; v[2 * k + 1] = (float)(uint8_t)(w >> 8);    // faster than PRMT + FADD on this path
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < 3 * N; ++k) raw[k] = __ldg(p + k);
+    for (int k = 0; k < 3 * N; ++k) v[k] = (float)__ldg(p + k);
   }
 #pragma unroll
-  for (int j = 0; j < N; ++j) { r[j] = (float)raw[3 * j]; g[j] = (float)raw[3 * j + 1]; b[j] = (float)raw[3 * j + 2]; }
+  for (int j = 0; j < N; ++j) { r[j] = v[3 * j]; g[j] = v[3 * j + 1]; b[j] = v[3 * j + 2]; }
 }
 
 template <int N, int AL4>

@@ -71,7 +71,11 @@ int tmf_device_count(void);
  * image, or a single shared map when wm_shared != 0.  Pixels outside whole
  * blocks (h%B, w%B strips) take the colour round trip only, as in the
  * reference.  alpha is double because the reference adds alpha*w in float64
- * (watermarking.py:198). */
+ * (watermarking.py:198).
+ * Environment (read once per process, at the first FAST embed): TMF_EMBED_TMA=1 routes
+ * 16-byte aligned batches (pointers, img_stride and 3*w multiples of 16; w/8 even and
+ * >= 32) through the TMA-staged kernel instead of the per-thread one - same results,
+ * measured slower; meant for A/B measurements. */
 int tmf_embed_rgb8(const uint8_t* rgb, uint8_t* out, int n, int h, int w, size_t img_stride,
                    const uint8_t* wm, int wm_shared, double alpha, int block, int mode, void* stream);
 

@@ -62,6 +62,9 @@ constexpr int kThreads = 128;
 #define TMF_EMBED_MIN_CTAS 5  // ... of the fast embed kernel: 5 since the subnormal quantiser (96 registers, 160 KB of stash
                               // leave the L1 60 KB for the pass-2 re-reads; profiles/r01_sweep_variants.txt, tables 4-5, 14)
 #endif
+#ifndef TMF_EMBED_ROWPTR
+#define TMF_EMBED_ROWPTR 0      // embed kernel's row addresses: 0 = base + i * pitch, 1 = running pointers
+#endif
 #ifndef TMF_EMBED_REPREFETCH
 #define TMF_EMBED_REPREFETCH 0  // ask L1 for the block's rows again before (1) / after (2) the eigen-solve
 #endif
@@ -138,10 +141,12 @@ struct BlockGeom {
   long long total_blocks;     // n * blocks_per_img  (< 2^31, make_geom)
   size_t img_stride;          // bytes between images
   size_t row_pitch;           // 3 * w
+  uint32_t pitch32;           // the same in 32 bits (make_geom: 3 * w < 2^32): row addresses by 32-bit increments
   FastDiv div_bpi, div_nbw;   // block index -> (image, block row, block column) without divisions
 };
 
-__device__ __forceinline__ size_t block_origin(const BlockGeom& g, long long gb, long long& img, int& by, int& bx) {
+__device__ __forceinline__ size_t block_origin(const BlockGeom& g, long long gb, long long& img, int& by, int& bx,
+                                               uint32_t* in_img = nullptr) {
   const uint32_t n = (uint32_t)gb;
   const uint32_t im = fastdiv(n, g.div_bpi);
   const uint32_t r = n - im * (uint32_t)g.blocks_per_img;
@@ -149,14 +154,16 @@ __device__ __forceinline__ size_t block_origin(const BlockGeom& g, long long gb,
   img = im;
   by = (int)y;
   bx = (int)(r - y * (uint32_t)g.nbw);
-  return (size_t)im * g.img_stride + (size_t)y * 8 * g.row_pitch + (size_t)bx * 24;
+  if (in_img) *in_img = r;                            // block index inside its image (the shared map's index)
+  // one 32x32->64 multiply per term (IMAD.WIDE.U32): no 64x64 products
+  return (size_t)im * g.img_stride + (unsigned long long)(y * 8u) * g.pitch32 + (uint32_t)bx * 24u;
 }
 
 // Ask for all 8 rows of a block up front.  The row loops below are rolled (small
 // code), so without this each warp would have only one row (3 loads) in flight.
-__device__ __forceinline__ void prefetch_block_rows(const uint8_t* __restrict__ base, size_t pitch) {
+__device__ __forceinline__ void prefetch_block_rows(const uint8_t* __restrict__ base, uint32_t pitch) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)i * pitch));
+  for (int i = 0; i < 8; ++i) { asm volatile("prefetch.global.L1 [%0];" ::"l"(base)); base += pitch; }
 }
 
 // Faithful-mode block I/O.  The DCT / Jacobi need the whole block in registers
@@ -207,7 +214,7 @@ k_embed_faithful(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, Blo
   const size_t org = block_origin(g, gb, img, by, bx);
   const uint8_t* src = rgb + org;
   float* col = sm + threadIdx.x;
-  prefetch_block_rows(src, g.row_pitch);
+  prefetch_block_rows(src, g.pitch32);
 
   float a[64], v[64];
   load_luma_block<VEC>(src, g.row_pitch, col, a);
@@ -281,8 +288,8 @@ k_extract_faithful(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ 
   const size_t org = block_origin(g, gb, img, by, bx);
   __shared__ float sm[64 * kThreads];
   float* col = sm + threadIdx.x;
-  prefetch_block_rows(wmk + org, g.row_pitch);
-  prefetch_block_rows(orig + org, g.row_pitch);
+  prefetch_block_rows(wmk + org, g.pitch32);
+  prefetch_block_rows(orig + org, g.pitch32);
   float sw = 0.0f, so = 0.0f;
 #pragma unroll 1
   for (int which = 0; which < 2; ++which) {          // one copy of the code for both images
@@ -517,9 +524,14 @@ __device__ __forceinline__ void gram_pairs_to_sym(const GramPairs& G, float (&gm
 // With KEEP, row i's luma is parked in shared memory as two float4 at
 // col[(2i) * STRIDE] and col[(2i+1) * STRIDE] (thread-private column,
 // conflict-free 128-bit accesses) for pass 2.
-template <int VEC, bool KEEP, int STRIDE = kThreads>
-__device__ __forceinline__ void gram_of_block(const uint8_t* __restrict__ base, size_t pitch, float (&gm)[36],
+// Row addressing follows the type of `pitch`: uint32_t = a running pointer (one 64-bit add per row;
+// k_extract_fast / k_sigma0_fast: +0.5 %), size_t = base + i * pitch (k_embed_fast, where the running
+// pointer measured 1.7 % slower - profiles/r01_sweep_variants.txt table 15).
+template <int VEC, bool KEEP, int STRIDE = kThreads, typename PITCH = uint32_t>
+__device__ __forceinline__ void gram_of_block(const uint8_t* __restrict__ base0, PITCH pitch, float (&gm)[36],
                                               float4* __restrict__ col = nullptr) {
+  constexpr bool kRunning = sizeof(PITCH) == 4;
+  const uint8_t* __restrict__ base = base0;
 #if TMF_USE_F32X2
   GramPairs G;
 #pragma unroll
@@ -532,7 +544,8 @@ __device__ __forceinline__ void gram_of_block(const uint8_t* __restrict__ base, 
   for (int i = 0; i < 8; ++i) {
     uint32_t w[6];
     float2 y2[4];
-    load_row24<VEC>(base + (size_t)i * pitch, w);
+    if (kRunning) { load_row24<VEC>(base, w); base += pitch; }
+    else load_row24<VEC>(base0 + (size_t)i * pitch, w);
     row_luma2(w, y2);
     if (KEEP) {
       col[(2 * i) * STRIDE] = make_float4(y2[0].x, y2[0].y, y2[1].x, y2[1].y);
@@ -548,7 +561,8 @@ __device__ __forceinline__ void gram_of_block(const uint8_t* __restrict__ base, 
   for (int i = 0; i < 8; ++i) {
     float y[8];
     uint32_t w[6];
-    load_row24<VEC>(base + (size_t)i * pitch, w);
+    if (kRunning) { load_row24<VEC>(base, w); base += pitch; }
+    else load_row24<VEC>(base0 + (size_t)i * pitch, w);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       // fma(c, 2^23 + b, -c 2^23) == RN(c b) exactly (one rounding of an exact sum), so the
@@ -730,7 +744,8 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
   const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (gb >= g.total_blocks) return;
   long long img; int by, bx;
-  const size_t org = block_origin(g, gb, img, by, bx);
+  uint32_t in_img;
+  const size_t org = block_origin(g, gb, img, by, bx, &in_img);
   const uint8_t* src = rgb + org;
 #if TMF_EMBED_STASH
   __shared__ float4 lum[16 * kThreads];      // 32 KB: the block's luma, thread-private column
@@ -738,24 +753,33 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
 #else
   float4* col = nullptr;                     // nothing parked: pass 2 recomputes the luma (8 IDP.2A per row)
 #endif
-  prefetch_block_rows(src, g.row_pitch);
+  prefetch_block_rows(src, g.pitch32);
   if (TMF_BULK_AHEAD > 0 && VEC == 8 && threadIdx.x == 0)
     bulk_prefetch_tile(rgb, g, ((long long)blockIdx.x + TMF_BULK_AHEAD) * kThreads);
-  const long long wi = (wm_shared ? 0 : img * g.blocks_per_img) + (long long)by * g.nbw + bx;
-  const uint32_t mark = (uint32_t)__ldg(wm + wi);
+  const uint32_t mark = (uint32_t)__ldg(wm + (wm_shared ? in_img : (uint32_t)gb));   // map index: 32 bits
   float w[8], f = 0.0f, c = 0.0f;
   if (mark != 0) {
     float gm[36];
+#if TMF_EMBED_ROWPTR
+    gram_of_block<VEC, TMF_EMBED_STASH != 0>(src, g.pitch32, gm, col);
+#else
     gram_of_block<VEC, TMF_EMBED_STASH != 0>(src, g.row_pitch, gm, col);
-    if (TMF_EMBED_REPREFETCH == 1) prefetch_block_rows(src, g.row_pitch);
+#endif
+    if (TMF_EMBED_REPREFETCH == 1) prefetch_block_rows(src, g.pitch32);
     tmf::embed_block_scalars_fast(gm, alpha, mark, w, f, c, nullptr, TMF_LUMA_UNIT);
-    if (TMF_EMBED_REPREFETCH == 2) prefetch_block_rows(src, g.row_pitch);
+    if (TMF_EMBED_REPREFETCH == 2) prefetch_block_rows(src, g.pitch32);
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) w[i] = 0.0f;
   }
-  // pass 2: the rows again (L1/L2 hits), rank-1 update, colour out, quantise, store
+  // pass 2: the rows again (L1/L2 hits), rank-1 update, colour out, quantise, store.
+  // (TMF_EMBED_ROWPTR = 1: one running pointer, the output row at `input row + (out - rgb)`, a
+  // warp-uniform distance: fewer address instructions, yet measured 1.7 % slower than base + i * pitch)
+#if TMF_EMBED_ROWPTR
+  const ptrdiff_t to_out = out - rgb;
+#else
   uint8_t* dst = out + org;
+#endif
 #if TMF_USE_F32X2
   const float2 w2[4] = {make_float2(w[0], w[1]), make_float2(w[2], w[3]), make_float2(w[4], w[5]), make_float2(w[6], w[7])};
 #endif
@@ -766,20 +790,31 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
     if (TMF_EMBED_STASH && mark != 0) { ya = col[(2 * i) * kThreads]; yb = col[(2 * i + 1) * kThreads]; }
 #if TMF_USE_F32X2
     uint32_t wd[6];
-    load_row24<VEC>(src + (size_t)i * g.row_pitch, wd);
+#if TMF_EMBED_ROWPTR
+    const uint8_t* rowp = src;
+#else
+    const uint8_t* rowp = src + (size_t)i * g.row_pitch;
+#endif
+    load_row24<VEC>(rowp, wd);
     float2 y2[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb.x, yb.y), make_float2(yb.z, yb.w)};
     if ((!TMF_EMBED_STASH && mark != 0) || (TMF_PASS2_IDP_PAIRS > 0 && mark == 0)) row_luma2(wd, y2);
     embed_row_fast2(wd, y2, w2, f, c, o);
 #else
     float r[8], gg[8], b[8];
     int q[24];
-    load_row_rgb255<VEC>(src + (size_t)i * g.row_pitch, r, gg, b);
+    const uint8_t* rowp = src + (size_t)i * g.row_pitch;
+    load_row_rgb255<VEC>(rowp, r, gg, b);
     const float y[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
     tmf::embed_row_fast(r, gg, b, y, w, f, c, q);
 #pragma unroll
     for (int k = 0; k < 6; ++k) o[k] = tmf::pack4_sat_u8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
 #endif
+#if TMF_EMBED_ROWPTR
+    store_row24<VEC>(const_cast<uint8_t*>(rowp) + to_out, o);
+    src += g.pitch32;
+#else
     store_row24<VEC>(dst + (size_t)i * g.row_pitch, o);
+#endif
   }
 }
 
@@ -924,8 +959,8 @@ k_extract_fast(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ orig
   if (gb >= g.total_blocks) return;
   long long img; int by, bx;
   const size_t org = block_origin(g, gb, img, by, bx);
-  prefetch_block_rows(wmk + org, g.row_pitch);
-  prefetch_block_rows(orig + org, g.row_pitch);
+  prefetch_block_rows(wmk + org, g.pitch32);
+  prefetch_block_rows(orig + org, g.pitch32);
   if (TMF_BULK_AHEAD > 0 && VEC == 8 && threadIdx.x == 0) {
     bulk_prefetch_tile(wmk, g, ((long long)blockIdx.x + TMF_BULK_AHEAD) * kThreads);
     bulk_prefetch_tile(orig, g, ((long long)blockIdx.x + TMF_BULK_AHEAD) * kThreads);
@@ -936,7 +971,7 @@ k_extract_fast(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ orig
 #pragma unroll 1
   for (int which = 0; which < 2; ++which) {
     float gm[36];
-    gram_of_block<VEC, false>((which == 0 ? wmk : orig) + org, g.row_pitch, gm);
+    gram_of_block<VEC, false>((which == 0 ? wmk : orig) + org, g.pitch32, gm);
     const float sg = tmf::sigma0_from_gram_fast(gm, nullptr, TMF_LUMA_UNIT);
     if (which == 0) sw = sg; else so = sg;
   }
@@ -951,8 +986,8 @@ k_sigma0_fast(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, Block
   long long img; int by, bx;
   const size_t org = block_origin(g, gb, img, by, bx);
   float gm[36];
-  prefetch_block_rows(rgb + org, g.row_pitch);
-  gram_of_block<VEC, false>(rgb + org, g.row_pitch, gm);
+  prefetch_block_rows(rgb + org, g.pitch32);
+  gram_of_block<VEC, false>(rgb + org, g.pitch32, gm);
   sigma0[gb] = tmf::sigma0_from_gram_fast(gm, nullptr, TMF_LUMA_UNIT);
 }
 
@@ -1303,6 +1338,8 @@ int make_geom(int n, int h, int w, size_t img_stride, int block, BlockGeom& g) {
   g.div_nbw = make_fastdiv((uint32_t)(g.nbw > 0 ? g.nbw : 1));
   g.img_stride = img_stride;
   g.row_pitch = (size_t)w * 3;
+  if (g.row_pitch > 0xffffffffull) return fail(TMF_ERR_BAD_ARG, "image rows of %zu bytes are not supported (limit 2^32 - 1)", g.row_pitch);
+  g.pitch32 = (uint32_t)g.row_pitch;
   return TMF_OK;
 }
 

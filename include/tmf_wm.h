@@ -106,6 +106,13 @@ int tmf_dct8x8_f32(const float* in, float* out, int64_t nblocks, int inverse, vo
 int tmf_rgb8_to_ycbcr_f32(const uint8_t* rgb, float* ycc, int64_t npixels, void* stream);
 int tmf_ycbcr_f32_to_rgb8(const float* ycc, uint8_t* rgb, int64_t npixels, void* stream);
 
+/* Pixel-format taps for the PIL boundary (image.convert("RGB"), watermarking.py:154,242-243, and
+ * Image.fromarray, :219): PIL stores an "RGB" image as 4 bytes per pixel (R, G, B, pad), and packing /
+ * unpacking that on the host costs ~25 ms per 4K image each way.  The host binding moves PIL's own
+ * layout and converts here.  rgbx: 16-byte aligned, rgb: 4-byte aligned; pad = the 4th byte written. */
+int tmf_rgbx8_to_rgb8(const uint8_t* rgbx, uint8_t* rgb, int64_t npixels, void* stream);
+int tmf_rgb8_to_rgbx8(const uint8_t* rgb, uint8_t* rgbx, int64_t npixels, int pad, void* stream);
+
 /* ---- watermark map on the device -------------------------------------------------------
  * resize_watermark (watermarking.py:86-132) after `.convert("L")`: PIL's LANCZOS resize of n
  * mode-"L" images (src_h x src_w bytes each, tightly packed rows, image k at src + k*src_stride)

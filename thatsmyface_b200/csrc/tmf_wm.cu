@@ -1319,6 +1319,52 @@ k_ycc2rgb(const float* __restrict__ ycc, uint8_t* __restrict__ rgb, long long np
 }
 
 // ---------------------------------------------------------------------------
+// Pixel-format taps for the PIL boundary.  PIL keeps an "RGB" image as 4 bytes per pixel
+// (R, G, B, pad); packing it to 3 bytes on the host (Image.tobytes) and unpacking the result
+// (Image.frombuffer) cost ~25 ms each for a 4K image - three orders of magnitude more than the
+// embed kernel.  The single-image API therefore moves PIL's own 4-byte layout over PCIe and
+// converts on the device: one thread per 4 pixels, 16 bytes <-> three words.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_rgbx_to_rgb(const uint8_t* __restrict__ rgbx, uint8_t* __restrict__ rgb, long long npx) {
+  const long long q = (long long)blockIdx.x * 256 + threadIdx.x;          // group of 4 pixels
+  const long long p0 = q * 4;
+  if (p0 >= npx) return;
+  if (p0 + 4 <= npx) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(rgbx) + q);      // x y z w = pixels 0..3, bytes R G B pad
+    uint32_t* o = reinterpret_cast<uint32_t*>(rgb) + q * 3;
+    o[0] = (v.x & 0x00ffffffu) | (v.y << 24);                              // R0 G0 B0 R1
+    o[1] = ((v.y >> 8) & 0x0000ffffu) | (v.z << 16);                       // G1 B1 R2 G2
+    o[2] = ((v.z >> 16) & 0x000000ffu) | (v.w << 8);                       // B2 R3 G3 B3
+  } else {
+    for (long long p = p0; p < npx; ++p)
+      for (int c = 0; c < 3; ++c) rgb[p * 3 + c] = rgbx[p * 4 + c];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_rgb_to_rgbx(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ rgbx, long long npx, uint32_t pad) {
+  const long long q = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long p0 = q * 4;
+  if (p0 >= npx) return;
+  if (p0 + 4 <= npx) {
+    const uint32_t* i = reinterpret_cast<const uint32_t*>(rgb) + q * 3;
+    const uint32_t a = __ldg(i), b = __ldg(i + 1), c = __ldg(i + 2), hi = pad << 24;
+    uint4 v;
+    v.x = (a & 0x00ffffffu) | hi;
+    v.y = (a >> 24) | ((b & 0x0000ffffu) << 8) | hi;
+    v.z = (b >> 16) | ((c & 0x000000ffu) << 16) | hi;
+    v.w = (c >> 8) | hi;
+    reinterpret_cast<uint4*>(rgbx)[q] = v;
+  } else {
+    for (long long p = p0; p < npx; ++p) {
+      for (int ch = 0; ch < 3; ++ch) rgbx[p * 4 + ch] = rgb[p * 3 + ch];
+      rgbx[p * 4 + 3] = (uint8_t)pad;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host-side helpers
 // ---------------------------------------------------------------------------
 int make_geom(int n, int h, int w, size_t img_stride, int block, BlockGeom& g) {
@@ -1564,6 +1610,24 @@ int tmf_rgb8_to_ycbcr_f32(const uint8_t* rgb, float* ycc, int64_t npixels, void*
   if (!rgb || !ycc) return fail(TMF_ERR_BAD_ARG, "null pointer");
   k_rgb2ycc<<<grid_for(npixels, 256), 256, 0, (cudaStream_t)stream>>>(rgb, ycc, npixels);
   return check_launch("rgb->ycbcr kernel launch");
+}
+
+int tmf_rgbx8_to_rgb8(const uint8_t* rgbx, uint8_t* rgb, int64_t npixels, void* stream) {
+  if (npixels < 0) return fail(TMF_ERR_BAD_ARG, "negative pixel count");
+  if (npixels == 0) return TMF_OK;
+  if (!rgbx || !rgb) return fail(TMF_ERR_BAD_ARG, "null pointer");
+  if (((uintptr_t)rgbx & 15) || ((uintptr_t)rgb & 3)) return fail(TMF_ERR_BAD_ARG, "rgbx must be 16-byte and rgb 4-byte aligned");
+  k_rgbx_to_rgb<<<grid_for((npixels + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(rgbx, rgb, npixels);
+  return check_launch("rgbx->rgb kernel launch");
+}
+
+int tmf_rgb8_to_rgbx8(const uint8_t* rgb, uint8_t* rgbx, int64_t npixels, int pad, void* stream) {
+  if (npixels < 0) return fail(TMF_ERR_BAD_ARG, "negative pixel count");
+  if (npixels == 0) return TMF_OK;
+  if (!rgbx || !rgb) return fail(TMF_ERR_BAD_ARG, "null pointer");
+  if (((uintptr_t)rgbx & 15) || ((uintptr_t)rgb & 3)) return fail(TMF_ERR_BAD_ARG, "rgbx must be 16-byte and rgb 4-byte aligned");
+  k_rgb_to_rgbx<<<grid_for((npixels + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(rgb, rgbx, npixels, (uint32_t)pad & 0xffu);
+  return check_launch("rgb->rgbx kernel launch");
 }
 
 int tmf_ycbcr_f32_to_rgb8(const float* ycc, uint8_t* rgb, int64_t npixels, void* stream) {

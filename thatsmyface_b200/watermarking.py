@@ -501,6 +501,134 @@ def _array_to_pil(arr, mode):
     return Image.frombuffer(mode, (w, h), arr, "raw", mode, 0, 1)
 
 
+# ---------------------------------------------------------------------------
+# PIL boundary of the single-image API, 4 bytes per pixel.
+#
+# PIL stores an "RGB" image as (R, G, B, pad) words.  ``Image.tobytes`` packs them to 3 bytes
+# and ``Image.frombuffer("RGB", ...)`` unpacks them again with per-pixel C loops: 25-28 ms
+# each for a 4K image, against 35 us for the embed kernel (BASELINE config 2).  With Pillow's
+# Arrow interface (>= 11.2) and pyarrow the 4-byte layout itself crosses the boundary:
+#   in : the image is pasted (a memcpy that releases the GIL) into a reusable single-block PIL
+#        image whose storage is exported zero-copy as a NumPy (H, W, 4) view and page-locked
+#        once; H2D of that; ``tmf_rgbx8_to_rgb8`` on the device;
+#   out: ``tmf_rgb8_to_rgbx8`` on the device; D2H; ``Image.fromarrow`` wraps the host buffer as
+#        a mode-"RGB" image without touching the pixels.
+# Host-side format plumbing only - the compute has no fallback; when the Arrow route is not
+# available the packed-bytes helpers above are used.
+# ---------------------------------------------------------------------------
+_pil_tls = threading.local()
+_FAST_PIL = None
+_STAGES_PER_THREAD = 4
+
+
+def _fast_pil():
+    """pyarrow module if the zero-copy PIL route is usable, else False."""
+    global _FAST_PIL
+    if _FAST_PIL is None:
+        try:
+            if os.environ.get("TMF_PIL_BOUNDARY", "").lower() == "bytes":
+                raise ImportError("disabled by TMF_PIL_BOUNDARY=bytes")
+            import pyarrow as pa
+
+            ok = hasattr(Image, "fromarrow") and hasattr(Image.core, "new_block") and hasattr(Image.Image, "__arrow_c_array__")
+            _FAST_PIL = pa if ok else False
+        except Exception:
+            _FAST_PIL = False
+    return _FAST_PIL
+
+
+class _Stage:
+    """Reusable single-block PIL "RGB" image + its zero-copy (H, W, 4) NumPy view, page-locked."""
+
+    def __init__(self, size, pin):
+        pa = _fast_pil()
+        w, h = size
+        self.core = Image.core.new_block("RGB", size)
+        self.img = Image.Image()._new(self.core)
+        self._arrow = pa.array(self.img)                       # zero-copy export of PIL's storage
+        self.view = self._arrow.flatten().to_numpy(zero_copy_only=True).reshape(h, w, 4)
+        self.event = None                                      # CUDA event of the last H2D out of this block
+        self._pinned = False
+        if pin:
+            lib = _lib.load()
+            if lib.tmf_pin_host(self.view.ctypes.data, self.view.nbytes) == 0:
+                self._pinned = True
+
+    def fill(self, image):
+        if self.event is not None:
+            self.event.synchronize()                           # the previous copy out of this block is done
+            self.event = None
+        image.load()
+        self.core.paste(image.im, (0, 0) + image.size)
+
+    def __del__(self):
+        if getattr(self, "_pinned", False):
+            try:
+                _lib.load().tmf_unpin_host(self.view.ctypes.data)
+            except Exception:
+                pass
+
+
+def _stage(size, slot, pin=True):
+    cache = getattr(_pil_tls, "stages", None)
+    if cache is None:
+        cache = _pil_tls.stages = collections.OrderedDict()
+    key = (size, slot)
+    st = cache.get(key)
+    if st is None:
+        while len(cache) >= _STAGES_PER_THREAD:
+            cache.popitem(last=False)
+        st = cache[key] = _Stage(size, pin)
+    else:
+        cache.move_to_end(key)
+    return st
+
+
+def _rgbx_array_to_pil(arr4):
+    """(H, W, 4) uint8 host array (R, G, B, pad) -> mode-"RGB" PIL image sharing its memory."""
+    pa = _fast_pil()
+    h, w = arr4.shape[:2]
+    fl = pa.FixedSizeListArray.from_arrays(pa.array(arr4.reshape(-1)), 4)
+    return Image.fromarrow(fl, "RGB", (w, h))
+
+
+def _pil_to_device_rgb(image, slot=0):
+    """PIL image of any mode -> CUDA uint8 (H, W, 3) tensor (image.convert("RGB"), watermarking.py:154)."""
+    torch = _torch()
+    if not _fast_pil():
+        return _to_device(_pil_to_rgb_array(image))
+    if image.mode != "RGB":
+        image = image.convert("RGB")
+    w, h = image.size
+    if w == 0 or h == 0:
+        return torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
+    st = _stage((w, h), slot)
+    st.fill(image)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)            # the exported view is read-only; it is only read
+        host4 = torch.from_numpy(st.view)
+    dev4 = host4.cuda(non_blocking=True)
+    st.event = torch.cuda.Event()
+    st.event.record()
+    dev3 = torch.empty((h, w, 3), dtype=torch.uint8, device=dev4.device)
+    _lib.check(_lib.load().tmf_rgbx8_to_rgb8(dev4.data_ptr(), dev3.data_ptr(), h * w, _stream_ptr(torch)))
+    return dev3
+
+
+def _device_rgb_to_pil(t):
+    """CUDA uint8 (H, W, 3) tensor -> new mode-"RGB" PIL image (Image.fromarray(...), watermarking.py:219)."""
+    torch = _torch()
+    if not _fast_pil() or t.numel() == 0:
+        return _array_to_pil(t.cpu().numpy(), "RGB")
+    h, w = t.shape[:2]
+    t = t.contiguous()
+    dev4 = torch.empty((h, w, 4), dtype=torch.uint8, device=t.device)
+    _lib.check(_lib.load().tmf_rgb8_to_rgbx8(t.data_ptr(), dev4.data_ptr(), h * w, 255, _stream_ptr(torch)))
+    return _rgbx_array_to_pil(dev4.cpu().numpy())
+
+
 def embed_watermark(image, watermark_data, preserve_ratio=False, custom_settings=None):
     """watermarking.py:135-221.  ``image``: PIL image of any mode;
     ``watermark_data``: PNG bytes or PIL image.  Returns a new PIL "RGB" image of
@@ -509,12 +637,11 @@ def embed_watermark(image, watermark_data, preserve_ratio=False, custom_settings
     torch = _torch()
     block_size, alpha, mode = _resolve(custom_settings)
     _require_supported_block(block_size)
-    rgb = _pil_to_rgb_array(image)
-    h, w = rgb.shape[:2]
-    x = _to_device(rgb)
+    x = _pil_to_device_rgb(image)
+    h, w = x.shape[:2]
     m = watermark_map(watermark_data, h // block_size, w // block_size, preserve_ratio, device=x.device)
     out = embed_tensor(x, m, alpha, block_size, mode)
-    return _array_to_pil(out.cpu().numpy(), "RGB")
+    return _device_rgb_to_pil(out)
 
 
 def extract_watermark(watermarked_image, original_image, custom_settings=None):
@@ -523,12 +650,13 @@ def extract_watermark(watermarked_image, original_image, custom_settings=None):
     torch = _torch()
     block_size, alpha, mode = _resolve(custom_settings)
     _require_supported_block(block_size)
-    a = _pil_to_rgb_array(watermarked_image)
-    b = _pil_to_rgb_array(original_image)
-    if a.shape != b.shape:
-        raise ValueError(f"watermarked image {a.shape[1]}x{a.shape[0]} and original image "
-                         f"{b.shape[1]}x{b.shape[0]} must have the same size")
-    out = extract_tensor(_to_device(a), _to_device(b), alpha, block_size, mode)
+    if watermarked_image.size != original_image.size:
+        (wa, ha), (wb, hb) = watermarked_image.size, original_image.size
+        raise ValueError(f"watermarked image {wa}x{ha} and original image "
+                         f"{wb}x{hb} must have the same size")
+    a = _pil_to_device_rgb(watermarked_image, 0)
+    b = _pil_to_device_rgb(original_image, 1)
+    out = extract_tensor(a, b, alpha, block_size, mode)
     return _array_to_pil(out.cpu().numpy(), "L")
 
 

@@ -21,19 +21,28 @@ SHAPES = [(1, 1), (7, 5), (64, 64), (135, 241), (1080, 1920)]
 def test_stage_view_is_pils_storage_and_is_reusable(shape):
     h, w = shape
     rng = np.random.default_rng(h * 1000 + w)
-    st = W._stage((w, h), 7, pin=False)
+    st = W._stage_acquire((w, h), pin=False)
     for _ in range(2):
         a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
         st.fill(Image.fromarray(a))
         assert st.view.shape == (h, w, 4) and (st.view[..., :3] == a).all()
-    assert W._stage((w, h), 7, pin=False) is st
+    W._stage_release(st)
+    again = W._stage_acquire((w, h), pin=False)
+    assert again is st                                    # the pool hands the same block out again
+    other = W._stage_acquire((w, h), pin=False)
+    assert other is not st                                # ... but never twice at the same time
+    W._stage_release(again)
+    W._stage_release(other)
 
 
 @needs_arrow
-def test_stage_cache_is_bounded_per_thread():
-    for k in range(3 * W._STAGES_PER_THREAD):
-        W._stage((8 + k, 8), 0, pin=False)
-    assert len(W._pil_tls.stages) <= W._STAGES_PER_THREAD
+def test_stage_pool_is_bounded(monkeypatch):
+    monkeypatch.setattr(W, "_STAGE_POOL_BYTES", 64 * 64 * 4 * 3)
+    held = [W._stage_acquire((64, 64), pin=False) for _ in range(8)]
+    for st in held:
+        W._stage_release(st)
+    assert W._stage_free_bytes <= W._STAGE_POOL_BYTES
+    assert sum(len(v) for v in W._stage_free.values()) <= 3 + 5      # other sizes may be pooled by other tests
 
 
 @needs_arrow

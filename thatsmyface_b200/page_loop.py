@@ -124,14 +124,25 @@ def embed_watermark_iter(images: Iterable, watermark_data, preserve_ratio: bool 
 
     def one(item):
         lane = pool.mine()
-        rgb = wmk._pil_to_rgb_array(_open(item))
-        h, w = rgb.shape[:2]
-        with torch.cuda.device(lane.device), torch.cuda.stream(lane.stream):
-            x = lane.upload("in", rgb)
-            m = wmk.watermark_map(watermark_data, h // block_size, w // block_size, preserve_ratio,
-                                  device=torch.device("cuda", lane.device))
-            out = lane.download("out", wmk.embed_tensor(x, m, alpha, block_size, mode))
-        result = wmk._array_to_pil(out, "RGB")
+        image = _open(item)
+        if wmk._fast_pil():
+            # PIL's 4-byte pixels cross PCIe as they are (watermarking.py, "PIL boundary"): the lane's
+            # thread owns its staging blocks, the conversions run on the lane's stream
+            with torch.cuda.device(lane.device), torch.cuda.stream(lane.stream):
+                x = wmk._pil_to_device_rgb(image)
+                h, w = x.shape[:2]
+                m = wmk.watermark_map(watermark_data, h // block_size, w // block_size, preserve_ratio,
+                                      device=torch.device("cuda", lane.device))
+                result = wmk._device_rgb_to_pil(wmk.embed_tensor(x, m, alpha, block_size, mode))
+        else:
+            rgb = wmk._pil_to_rgb_array(image)
+            h, w = rgb.shape[:2]
+            with torch.cuda.device(lane.device), torch.cuda.stream(lane.stream):
+                x = lane.upload("in", rgb)
+                m = wmk.watermark_map(watermark_data, h // block_size, w // block_size, preserve_ratio,
+                                      device=torch.device("cuda", lane.device))
+                out = lane.download("out", wmk.embed_tensor(x, m, alpha, block_size, mode))
+            result = wmk._array_to_pil(out, "RGB")
         if not png:
             return result
         buf = io.BytesIO()
@@ -164,6 +175,15 @@ def extract_watermark_iter(pairs: Iterable[Tuple], custom_settings=None, *, lane
 
     def one(pair):
         lane = pool.mine()
+        if wmk._fast_pil():
+            ia, ib = _open(pair[0]), _open(pair[1])
+            if ia.size != ib.size:
+                raise ValueError(f"watermarked image {ia.size[0]}x{ia.size[1]} and original image "
+                                 f"{ib.size[0]}x{ib.size[1]} must have the same size")
+            with torch.cuda.device(lane.device), torch.cuda.stream(lane.stream):
+                out = lane.download("out", wmk.extract_tensor(wmk._pil_to_device_rgb(ia), wmk._pil_to_device_rgb(ib),
+                                                               alpha, block_size, mode))
+            return wmk._array_to_pil(out, "L")
         a = wmk._pil_to_rgb_array(_open(pair[0]))
         b = wmk._pil_to_rgb_array(_open(pair[1]))
         if a.shape != b.shape:

@@ -509,16 +509,18 @@ def _array_to_pil(arr, mode):
 # each for a 4K image, against 35 us for the embed kernel (BASELINE config 2).  With Pillow's
 # Arrow interface (>= 11.2) and pyarrow the 4-byte layout itself crosses the boundary:
 #   in : the image is pasted (a memcpy that releases the GIL) into a reusable single-block PIL
-#        image whose storage is exported zero-copy as a NumPy (H, W, 4) view and page-locked
-#        once; H2D of that; ``tmf_rgbx8_to_rgb8`` on the device;
+#        image (process-wide pool) whose storage is exported zero-copy as a NumPy (H, W, 4) view
+#        and page-locked once; H2D of that; ``tmf_rgbx8_to_rgb8`` on the device;
 #   out: ``tmf_rgb8_to_rgbx8`` on the device; D2H; ``Image.fromarrow`` wraps the host buffer as
 #        a mode-"RGB" image without touching the pixels.
 # Host-side format plumbing only - the compute has no fallback; when the Arrow route is not
 # available the packed-bytes helpers above are used.
 # ---------------------------------------------------------------------------
-_pil_tls = threading.local()
 _FAST_PIL = None
-_STAGES_PER_THREAD = 4
+_STAGE_POOL_BYTES = 512 << 20          # page-locked staging kept for reuse, all threads together
+_stage_lock = threading.Lock()
+_stage_free = collections.OrderedDict()   # (w, h) -> [free _Stage, ...], least recently used size first
+_stage_free_bytes = 0
 
 
 def _fast_pil():
@@ -569,19 +571,39 @@ class _Stage:
                 pass
 
 
-def _stage(size, slot, pin=True):
-    cache = getattr(_pil_tls, "stages", None)
-    if cache is None:
-        cache = _pil_tls.stages = collections.OrderedDict()
-    key = (size, slot)
-    st = cache.get(key)
-    if st is None:
-        while len(cache) >= _STAGES_PER_THREAD:
-            cache.popitem(last=False)
-        st = cache[key] = _Stage(size, pin)
-    else:
-        cache.move_to_end(key)
-    return st
+def _stage_acquire(size, pin=True):
+    """A staging block of this size for the calling thread: a free one of the process-wide pool
+    (threads come and go - the page loop's lanes are a fresh thread pool per call - but page-locking
+    a block costs milliseconds and is serialised by the driver) or a new one."""
+    global _stage_free_bytes
+    with _stage_lock:
+        lst = _stage_free.get(size)
+        if lst:
+            st = lst.pop()
+            _stage_free_bytes -= st.view.nbytes
+            if not lst:
+                del _stage_free[size]
+            return st
+    return _Stage(size, pin)
+
+
+def _stage_release(st):
+    """Back to the pool (its pending H2D, if any, is waited for by the next ``fill``)."""
+    global _stage_free_bytes
+    dropped = []
+    with _stage_lock:
+        size = (st.view.shape[1], st.view.shape[0])
+        _stage_free.setdefault(size, []).append(st)
+        _stage_free.move_to_end(size)
+        _stage_free_bytes += st.view.nbytes
+        while _stage_free_bytes > _STAGE_POOL_BYTES and _stage_free:
+            old_size, lst = next(iter(_stage_free.items()))
+            victim = lst.pop(0)
+            _stage_free_bytes -= victim.view.nbytes
+            if not lst:
+                del _stage_free[old_size]
+            dropped.append(victim)
+    del dropped                                                 # unpinned outside the lock
 
 
 def _rgbx_array_to_pil(arr4):
@@ -592,7 +614,7 @@ def _rgbx_array_to_pil(arr4):
     return Image.fromarrow(fl, "RGB", (w, h))
 
 
-def _pil_to_device_rgb(image, slot=0):
+def _pil_to_device_rgb(image):
     """PIL image of any mode -> CUDA uint8 (H, W, 3) tensor (image.convert("RGB"), watermarking.py:154)."""
     torch = _torch()
     if not _fast_pil():
@@ -602,16 +624,19 @@ def _pil_to_device_rgb(image, slot=0):
     w, h = image.size
     if w == 0 or h == 0:
         return torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
-    st = _stage((w, h), slot)
-    st.fill(image)
     import warnings
 
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore", UserWarning)            # the exported view is read-only; it is only read
-        host4 = torch.from_numpy(st.view)
-    dev4 = host4.cuda(non_blocking=True)
-    st.event = torch.cuda.Event()
-    st.event.record()
+    st = _stage_acquire((w, h))
+    try:
+        st.fill(image)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)        # the exported view is read-only; it is only read
+            host4 = torch.from_numpy(st.view)
+        dev4 = host4.cuda(non_blocking=True)
+        st.event = torch.cuda.Event()
+        st.event.record()
+    finally:
+        _stage_release(st)
     dev3 = torch.empty((h, w, 3), dtype=torch.uint8, device=dev4.device)
     _lib.check(_lib.load().tmf_rgbx8_to_rgb8(dev4.data_ptr(), dev3.data_ptr(), h * w, _stream_ptr(torch)))
     return dev3
@@ -654,8 +679,8 @@ def extract_watermark(watermarked_image, original_image, custom_settings=None):
         (wa, ha), (wb, hb) = watermarked_image.size, original_image.size
         raise ValueError(f"watermarked image {wa}x{ha} and original image "
                          f"{wb}x{hb} must have the same size")
-    a = _pil_to_device_rgb(watermarked_image, 0)
-    b = _pil_to_device_rgb(original_image, 1)
+    a = _pil_to_device_rgb(watermarked_image)
+    b = _pil_to_device_rgb(original_image)
     out = extract_tensor(a, b, alpha, block_size, mode)
     return _array_to_pil(out.cpu().numpy(), "L")
 

@@ -14,13 +14,15 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
-VARIANTS = {          # the last sweep of round 1 (table 14 of r01_sweep_variants.txt); edit for the next one
+VARIANTS = {          # the last sweeps of round 1 (tables 14-15 of r01_sweep_variants.txt); edit for the next one
     "base": {},
     "c6": {"TMF_EMBED_MIN_CTAS": 6},
     "c4": {"TMF_EMBED_MIN_CTAS": 4},
     "biasq": {"TMF_QUANT_DENORM": 0},
     "stash0": {"TMF_EMBED_STASH": 0},
     "rp1": {"TMF_EMBED_REPREFETCH": 1},
+    "rowptr": {"TMF_EMBED_ROWPTR": 1},
+    "p2u2": {"TMF_ROW_UNROLL_P2": 2},
     "x5": {"TMF_FAST_MIN_CTAS": 5},
 }
 

@@ -72,6 +72,10 @@ constexpr int kThreads = 128;
 #define TMF_EMBED_STASH 1     // 1: pass 1 parks the luma in shared memory for pass 2; 0: pass 2 recomputes it
 #endif
 constexpr int kRowUnroll = TMF_ROW_UNROLL;
+#ifndef TMF_ROW_UNROLL_P2
+#define TMF_ROW_UNROLL_P2 TMF_ROW_UNROLL   // the embed kernel's pass 2, separately
+#endif
+constexpr int kRowUnrollP2 = TMF_ROW_UNROLL_P2;
 
 // ---------------------------------------------------------------------------
 // 24-byte block-row load/store with the widest access the alignment allows
@@ -783,7 +787,7 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
 #if TMF_USE_F32X2
   const float2 w2[4] = {make_float2(w[0], w[1]), make_float2(w[2], w[3]), make_float2(w[4], w[5]), make_float2(w[6], w[7])};
 #endif
-#pragma unroll kRowUnroll
+#pragma unroll kRowUnrollP2
   for (int i = 0; i < 8; ++i) {
     uint32_t o[6];
     float4 ya = make_float4(0.f, 0.f, 0.f, 0.f), yb = ya;

@@ -165,9 +165,13 @@ __device__ __forceinline__ size_t block_origin(const BlockGeom& g, long long gb,
 
 // Ask for all 8 rows of a block up front.  The row loops below are rolled (small
 // code), so without this each warp would have only one row (3 loads) in flight.
-__device__ __forceinline__ void prefetch_block_rows(const uint8_t* __restrict__ base, uint32_t pitch) {
+#ifndef TMF_PREFETCH_FROM
+#define TMF_PREFETCH_FROM 0   // first row asked for by the fast kernels' entry prefetch (the row loops load rows 0..3 at once anyway)
+#endif
+__device__ __forceinline__ void prefetch_block_rows(const uint8_t* __restrict__ base, uint32_t pitch, int from = 0) {
+  base += (size_t)from * pitch;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { asm volatile("prefetch.global.L1 [%0];" ::"l"(base)); base += pitch; }
+  for (int i = from; i < 8; ++i) { asm volatile("prefetch.global.L1 [%0];" ::"l"(base)); base += pitch; }
 }
 
 // Faithful-mode block I/O.  The DCT / Jacobi need the whole block in registers
@@ -757,7 +761,7 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
 #else
   float4* col = nullptr;                     // nothing parked: pass 2 recomputes the luma (8 IDP.2A per row)
 #endif
-  prefetch_block_rows(src, g.pitch32);
+  prefetch_block_rows(src, g.pitch32, TMF_PREFETCH_FROM);
   if (TMF_BULK_AHEAD > 0 && VEC == 8 && threadIdx.x == 0)
     bulk_prefetch_tile(rgb, g, ((long long)blockIdx.x + TMF_BULK_AHEAD) * kThreads);
   const uint32_t mark = (uint32_t)__ldg(wm + (wm_shared ? in_img : (uint32_t)gb));   // map index: 32 bits
@@ -963,7 +967,7 @@ k_extract_fast(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ orig
   if (gb >= g.total_blocks) return;
   long long img; int by, bx;
   const size_t org = block_origin(g, gb, img, by, bx);
-  prefetch_block_rows(wmk + org, g.pitch32);
+  prefetch_block_rows(wmk + org, g.pitch32, TMF_PREFETCH_FROM);
   prefetch_block_rows(orig + org, g.pitch32);
   if (TMF_BULK_AHEAD > 0 && VEC == 8 && threadIdx.x == 0) {
     bulk_prefetch_tile(wmk, g, ((long long)blockIdx.x + TMF_BULK_AHEAD) * kThreads);

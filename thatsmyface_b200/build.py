@@ -16,6 +16,9 @@ LIBDIR = os.path.join(PKG, "lib")
 LIBPATH = os.path.join(LIBDIR, "libtmfwm.so")
 SOURCES = ["tmf_wm.cu"]
 
+# Never add --use_fast_math / -ftz=true here: the fast embed kernel's quantiser floors onto
+# SUBNORMAL floats (the integer level is the float's bit pattern, csrc/tmf_wm.cu embed_row_fast2);
+# flushing them to zero would zero every output pixel (tests/test_gpu_parity.py fails at once).
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

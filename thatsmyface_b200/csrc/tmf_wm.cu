@@ -62,6 +62,9 @@ constexpr int kThreads = 128;
 #define TMF_EMBED_MIN_CTAS 5  // ... of the fast embed kernel: 5 since the subnormal quantiser (96 registers, 160 KB of stash
                               // leave the L1 60 KB for the pass-2 re-reads; profiles/r01_sweep_variants.txt, tables 4-5, 14)
 #endif
+#ifndef TMF_EMBED_PERSIST
+#define TMF_EMBED_PERSIST 0     // > 0: persistent embed kernel with that many CTAs per SM and a next-block L2 prefetch
+#endif
 #ifndef TMF_EMBED_ROWPTR
 #define TMF_EMBED_ROWPTR 0      // embed kernel's row addresses: 0 = base + i * pitch, 1 = running pointers
 #endif
@@ -749,19 +752,35 @@ template <int VEC>
 __global__ void __launch_bounds__(kThreads, TMF_EMBED_MIN_CTAS)
 k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGeom g,
              const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
-  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (gb >= g.total_blocks) return;
-  long long img; int by, bx;
-  uint32_t in_img;
-  const size_t org = block_origin(g, gb, img, by, bx, &in_img);
-  const uint8_t* src = rgb + org;
 #if TMF_EMBED_STASH
   __shared__ float4 lum[16 * kThreads];      // 32 KB: the block's luma, thread-private column
   float4* col = lum + threadIdx.x;
 #else
   float4* col = nullptr;                     // nothing parked: pass 2 recomputes the luma (8 IDP.2A per row)
 #endif
+#if TMF_EMBED_PERSIST
+  // persistent form: the grid is TMF_EMBED_PERSIST CTAs per SM, a thread walks blocks gb, gb + stride, ...
+  // and asks L2 for its NEXT block's rows while it works on this one
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long gb = (long long)blockIdx.x * kThreads + threadIdx.x; gb < g.total_blocks; gb += stride) {
+#else
+  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (gb >= g.total_blocks) return;
+  {
+#endif
+  long long img; int by, bx;
+  uint32_t in_img;
+  const size_t org = block_origin(g, gb, img, by, bx, &in_img);
+  const uint8_t* src = rgb + org;
   prefetch_block_rows(src, g.pitch32, TMF_PREFETCH_FROM);
+#if TMF_EMBED_PERSIST
+  if (gb + stride < g.total_blocks) {
+    long long i2; int y2, x2;
+    const uint8_t* nxt = rgb + block_origin(g, gb + stride, i2, y2, x2);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt)); nxt += g.pitch32; }
+  }
+#endif
   if (TMF_BULK_AHEAD > 0 && VEC == 8 && threadIdx.x == 0)
     bulk_prefetch_tile(rgb, g, ((long long)blockIdx.x + TMF_BULK_AHEAD) * kThreads);
   const uint32_t mark = (uint32_t)__ldg(wm + (wm_shared ? in_img : (uint32_t)gb));   // map index: 32 bits
@@ -824,6 +843,7 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
     store_row24<VEC>(dst + (size_t)i * g.row_pitch, o);
 #endif
   }
+  }   // blocks of this thread
 }
 
 
@@ -1433,6 +1453,18 @@ int tma_kernel_attrs() {
 
 unsigned grid_for(long long items, int per_cta) { return (unsigned)((items + per_cta - 1) / per_cta); }
 
+// grid of the fast embed kernel: one CTA per 128 blocks, or (TMF_EMBED_PERSIST) a fixed number per SM
+unsigned embed_grid(unsigned tiles) {
+#if TMF_EMBED_PERSIST
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned cap = (unsigned)sms * TMF_EMBED_PERSIST;
+  return tiles < cap ? tiles : cap;
+#else
+  return tiles;
+#endif
+}
+
 
 // dispatch over the block sizes other than 8
 // Dispatch over the block sizes other than 8.  f(N, A) gets integral constants: N = block
@@ -1505,9 +1537,9 @@ int tmf_embed_rgb8(const uint8_t* rgb, uint8_t* out, int n, int h, int w, size_t
       k_embed_fast_tma<<<grid, kThreads, kEmbedTmaSmem, st>>>(rgb, out, g, wm, wm_shared, alpha);
     } else if (mode == TMF_MODE_FAST) {
       switch (vec) {
-        case 8: k_embed_fast<8><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
-        case 4: k_embed_fast<4><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
-        default: k_embed_fast<1><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
+        case 8: k_embed_fast<8><<<embed_grid(grid), kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
+        case 4: k_embed_fast<4><<<embed_grid(grid), kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
+        default: k_embed_fast<1><<<embed_grid(grid), kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
       }
     } else {
       switch (vec) {

@@ -24,6 +24,7 @@ VARIANTS = {          # the last sweeps of round 1 (tables 14-15 of r01_sweep_va
     "rowptr": {"TMF_EMBED_ROWPTR": 1},
     "p2u2": {"TMF_ROW_UNROLL_P2": 2},
     "x5": {"TMF_FAST_MIN_CTAS": 5},
+    "t128": {"TMF_EMBED_THREADS": 128, "TMF_EXTRACT_THREADS": 128},
     "persist5": {"TMF_EMBED_PERSIST": 5},
 }
 

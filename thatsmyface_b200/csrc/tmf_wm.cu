@@ -62,6 +62,20 @@ constexpr int kThreads = 128;
 #define TMF_EMBED_MIN_CTAS 5  // ... of the fast embed kernel: 5 since the subnormal quantiser (96 registers, 160 KB of stash
                               // leave the L1 60 KB for the pass-2 re-reads; profiles/r01_sweep_variants.txt, tables 4-5, 14)
 #endif
+#ifndef TMF_EMBED_THREADS
+#define TMF_EMBED_THREADS 32    // threads per CTA of the fast embed kernel (128, 64 or 32; same warps per SM): one-warp CTAs
+                                // release their registers and stash as soon as their own warp ends (+1 %, table 16)
+#endif
+constexpr int kEmbedThreads = TMF_EMBED_THREADS;
+#ifdef TMF_EMBED_MIN_CTAS_RAW
+constexpr int kEmbedMinCtas = TMF_EMBED_MIN_CTAS_RAW;          // CTAs of kEmbedThreads threads per SM
+#else
+constexpr int kEmbedMinCtas = TMF_EMBED_MIN_CTAS * (128 / TMF_EMBED_THREADS);
+#endif
+#ifndef TMF_EXTRACT_THREADS
+#define TMF_EXTRACT_THREADS 32  // threads per CTA of the fast extract kernel (+0.5 %)
+#endif
+constexpr int kExtractThreads = TMF_EXTRACT_THREADS;
 #ifndef TMF_EMBED_PERSIST
 #define TMF_EMBED_PERSIST 0     // > 0: persistent embed kernel with that many CTAs per SM and a next-block L2 prefetch
 #endif
@@ -749,11 +763,11 @@ __device__ __forceinline__ void embed_row_fast2(const uint32_t (&w)[6], const fl
 // 24-byte row pieces cost more L1 wavefronts than the skipped work saves
 // (profiles/r01_sweep_variants.txt, third table).
 template <int VEC>
-__global__ void __launch_bounds__(kThreads, TMF_EMBED_MIN_CTAS)
+__global__ void __launch_bounds__(kEmbedThreads, kEmbedMinCtas)
 k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGeom g,
              const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
 #if TMF_EMBED_STASH
-  __shared__ float4 lum[16 * kThreads];      // 32 KB: the block's luma, thread-private column
+  __shared__ float4 lum[16 * kEmbedThreads];      // 32 KB: the block's luma, thread-private column
   float4* col = lum + threadIdx.x;
 #else
   float4* col = nullptr;                     // nothing parked: pass 2 recomputes the luma (8 IDP.2A per row)
@@ -761,10 +775,10 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
 #if TMF_EMBED_PERSIST
   // persistent form: the grid is TMF_EMBED_PERSIST CTAs per SM, a thread walks blocks gb, gb + stride, ...
   // and asks L2 for its NEXT block's rows while it works on this one
-  const long long stride = (long long)gridDim.x * kThreads;
-  for (long long gb = (long long)blockIdx.x * kThreads + threadIdx.x; gb < g.total_blocks; gb += stride) {
+  const long long stride = (long long)gridDim.x * kEmbedThreads;
+  for (long long gb = (long long)blockIdx.x * kEmbedThreads + threadIdx.x; gb < g.total_blocks; gb += stride) {
 #else
-  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long gb = (long long)blockIdx.x * kEmbedThreads + threadIdx.x;
   if (gb >= g.total_blocks) return;
   {
 #endif
@@ -782,15 +796,15 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
   }
 #endif
   if (TMF_BULK_AHEAD > 0 && VEC == 8 && threadIdx.x == 0)
-    bulk_prefetch_tile(rgb, g, ((long long)blockIdx.x + TMF_BULK_AHEAD) * kThreads);
+    bulk_prefetch_tile(rgb, g, ((long long)blockIdx.x + TMF_BULK_AHEAD) * kEmbedThreads);
   const uint32_t mark = (uint32_t)__ldg(wm + (wm_shared ? in_img : (uint32_t)gb));   // map index: 32 bits
   float w[8], f = 0.0f, c = 0.0f;
   if (mark != 0) {
     float gm[36];
 #if TMF_EMBED_ROWPTR
-    gram_of_block<VEC, TMF_EMBED_STASH != 0>(src, g.pitch32, gm, col);
+    gram_of_block<VEC, TMF_EMBED_STASH != 0, kEmbedThreads>(src, g.pitch32, gm, col);
 #else
-    gram_of_block<VEC, TMF_EMBED_STASH != 0>(src, g.row_pitch, gm, col);
+    gram_of_block<VEC, TMF_EMBED_STASH != 0, kEmbedThreads, size_t>(src, g.row_pitch, gm, col);
 #endif
     if (TMF_EMBED_REPREFETCH == 1) prefetch_block_rows(src, g.pitch32);
     tmf::embed_block_scalars_fast(gm, alpha, mark, w, f, c, nullptr, TMF_LUMA_UNIT);
@@ -814,7 +828,7 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
   for (int i = 0; i < 8; ++i) {
     uint32_t o[6];
     float4 ya = make_float4(0.f, 0.f, 0.f, 0.f), yb = ya;
-    if (TMF_EMBED_STASH && mark != 0) { ya = col[(2 * i) * kThreads]; yb = col[(2 * i + 1) * kThreads]; }
+    if (TMF_EMBED_STASH && mark != 0) { ya = col[(2 * i) * kEmbedThreads]; yb = col[(2 * i + 1) * kEmbedThreads]; }
 #if TMF_USE_F32X2
     uint32_t wd[6];
 #if TMF_EMBED_ROWPTR
@@ -980,10 +994,10 @@ k_embed_fast_tma(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, Blo
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kThreads, TMF_FAST_MIN_CTAS)
+__global__ void __launch_bounds__(kExtractThreads, TMF_FAST_MIN_CTAS * (128 / TMF_EXTRACT_THREADS))
 k_extract_fast(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ orig, uint8_t* __restrict__ out_wm,
                BlockGeom g, double alpha) {
-  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long gb = (long long)blockIdx.x * kExtractThreads + threadIdx.x;
   if (gb >= g.total_blocks) return;
   long long img; int by, bx;
   const size_t org = block_origin(g, gb, img, by, bx);
@@ -1532,14 +1546,15 @@ int tmf_embed_rgb8(const uint8_t* rgb, uint8_t* out, int n, int h, int w, size_t
   } else if (g.total_blocks > 0) {
     const unsigned grid = grid_for(g.total_blocks, kThreads);
     const int vec = pick_vec(g, rgb, out);
+    const unsigned egrid = grid_for(g.total_blocks, kEmbedThreads);
     if (mode == TMF_MODE_FAST && tma_ok(g, rgb, out)) {
       if (int rc = tma_kernel_attrs()) return rc;
       k_embed_fast_tma<<<grid, kThreads, kEmbedTmaSmem, st>>>(rgb, out, g, wm, wm_shared, alpha);
     } else if (mode == TMF_MODE_FAST) {
       switch (vec) {
-        case 8: k_embed_fast<8><<<embed_grid(grid), kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
-        case 4: k_embed_fast<4><<<embed_grid(grid), kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
-        default: k_embed_fast<1><<<embed_grid(grid), kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
+        case 8: k_embed_fast<8><<<embed_grid(egrid), kEmbedThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
+        case 4: k_embed_fast<4><<<embed_grid(egrid), kEmbedThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
+        default: k_embed_fast<1><<<embed_grid(egrid), kEmbedThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
       }
     } else {
       switch (vec) {
@@ -1575,11 +1590,12 @@ int tmf_extract_rgb8(const uint8_t* wmk_rgb, const uint8_t* orig_rgb, uint8_t* o
     return check_launch("extract kernel launch");
   }
   const int vec = pick_vec(g, wmk_rgb, orig_rgb);
+  const unsigned xgrid = grid_for(g.total_blocks, kExtractThreads);
   if (mode == TMF_MODE_FAST) {
     switch (vec) {
-      case 8: k_extract_fast<8><<<grid, kThreads, 0, st>>>(wmk_rgb, orig_rgb, out_wm, g, alpha); break;
-      case 4: k_extract_fast<4><<<grid, kThreads, 0, st>>>(wmk_rgb, orig_rgb, out_wm, g, alpha); break;
-      default: k_extract_fast<1><<<grid, kThreads, 0, st>>>(wmk_rgb, orig_rgb, out_wm, g, alpha); break;
+      case 8: k_extract_fast<8><<<xgrid, kExtractThreads, 0, st>>>(wmk_rgb, orig_rgb, out_wm, g, alpha); break;
+      case 4: k_extract_fast<4><<<xgrid, kExtractThreads, 0, st>>>(wmk_rgb, orig_rgb, out_wm, g, alpha); break;
+      default: k_extract_fast<1><<<xgrid, kExtractThreads, 0, st>>>(wmk_rgb, orig_rgb, out_wm, g, alpha); break;
     }
   } else {
     switch (vec) {

@@ -62,6 +62,9 @@ constexpr int kThreads = 128;
 #define TMF_EMBED_MIN_CTAS 5  // ... of the fast embed kernel: 5 since the subnormal quantiser (96 registers, 160 KB of stash
                               // leave the L1 60 KB for the pass-2 re-reads; profiles/r01_sweep_variants.txt, tables 4-5, 14)
 #endif
+#ifndef TMF_STORE_HINT
+#define TMF_STORE_HINT 0        // 8-byte row stores: 0 = plain, 1 = st.global.cs (streaming), 2 = st.global.wt
+#endif
 #ifndef TMF_EMBED_THREADS
 #define TMF_EMBED_THREADS 32    // threads per CTA of the fast embed kernel (128, 64 or 32; same warps per SM): one-warp CTAs
                                 // release their registers and stash as soon as their own warp ends (+1 %, table 16)
@@ -122,7 +125,13 @@ __device__ __forceinline__ void load_row24(const uint8_t* __restrict__ p, uint32
 
 template <int VEC>
 __device__ __forceinline__ void store_row24(uint8_t* __restrict__ p, const uint32_t (&w)[6]) {
-  if (VEC == 8 || VEC == 0) {
+  if (VEC == 8 && TMF_STORE_HINT == 1) {            // streaming stores: the output is never read again
+    uint2* q = reinterpret_cast<uint2*>(p);
+    __stcs(q, make_uint2(w[0], w[1])); __stcs(q + 1, make_uint2(w[2], w[3])); __stcs(q + 2, make_uint2(w[4], w[5]));
+  } else if (VEC == 8 && TMF_STORE_HINT == 2) {
+    uint2* q = reinterpret_cast<uint2*>(p);
+    __stwt(q, make_uint2(w[0], w[1])); __stwt(q + 1, make_uint2(w[2], w[3])); __stwt(q + 2, make_uint2(w[4], w[5]));
+  } else if (VEC == 8 || VEC == 0) {
     uint2* q = reinterpret_cast<uint2*>(p);
     q[0] = make_uint2(w[0], w[1]); q[1] = make_uint2(w[2], w[3]); q[2] = make_uint2(w[4], w[5]);
   } else if (VEC == 4) {

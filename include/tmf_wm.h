@@ -51,8 +51,13 @@ enum {
 enum {
   TMF_MODE_FAITHFUL = 0, /* DCT -> full one-sided Jacobi SVD -> sigma0 += alpha*w -> U S' V^T -> IDCT,
                             colour math bit-exact with the reference's float64 dot */
-  TMF_MODE_FAST = 1      /* algebraically reduced: top singular triplet of the spatial block and a
-                            rank-1 update (orthonormal DCT preserves singular values); fp32 colour */
+  TMF_MODE_FAST = 1,     /* algebraically reduced: top singular triplet of the spatial block and a
+                            rank-1 update (orthonormal DCT preserves singular values; NO DCT and NO SVD
+                            are executed); fp32 colour */
+  TMF_MODE_LITERAL = 2   /* block size 8 only: FAITHFUL with the literal U diag(S') V^T product and IDCT
+                            (V accumulated by the Jacobi).  FAITHFUL itself uses the identity
+                            U diag(S') V^T = D + (S'[0] - S[0]) u0 v0^T, v0 = D^T u0 / S[0] - the same
+                            matrix, without V.  For extract / sigma0 LITERAL equals FAITHFUL. */
 };
 
 int tmf_version(void);
@@ -61,9 +66,13 @@ const char* tmf_last_error(void);
 /* Number of CUDA devices visible, or a negative error. */
 int tmf_device_count(void);
 
-/* `block` is the reference's block_size: 8 runs the tuned kernels (both modes); the
- * other even sizes 4..16 run a generic kernel that uses the FAST algebra whatever `mode`
- * says.  Below, B = block.
+/* Which kernel the calling thread's last FAST block-8 embed / extract took:
+ * 1 = TMA-tiled persistent kernel, 0 = per-thread kernel. */
+int tmf_last_fast_path(void);
+
+/* `block` is the reference's block_size (any even size 4..16, the range of its UI); both modes
+ * honour every size (8 = BLOCK_SIZE runs the tuned kernels).  Below, B = block.
+ * Limits per call: n * (h/B) * (w/B) < 2^31 blocks, 3*w < 2^32 bytes per row (TMF_ERR_BAD_ARG).
  *
  * embed_watermark on a batch.  rgb/out: n images of h x w x 3 bytes (out may not
  * alias rgb).  wm: watermark map(s), (h/B) x (w/B) bytes each, already resized
@@ -72,10 +81,10 @@ int tmf_device_count(void);
  * blocks (h%B, w%B strips) take the colour round trip only, as in the
  * reference.  alpha is double because the reference adds alpha*w in float64
  * (watermarking.py:198).
- * Environment (read once per process, at the first FAST embed): TMF_EMBED_TMA=1 routes
- * 16-byte aligned batches (pointers, img_stride and 3*w multiples of 16; w/8 even and
- * >= 32) through the TMA-staged kernel instead of the per-thread one - same results,
- * measured slower; meant for A/B measurements. */
+ * FAST mode, block 8: batches whose pointers, img_stride and 3*w are multiples of 16 and whose rows
+ * hold a multiple of 16 blocks (w % 128 == 0: 512, 1280, 1920, 3840, 7680 ...) run the TMA-tiled
+ * persistent kernel; everything else the per-thread kernel - same results (tmf_last_fast_path()).
+ * TMF_NO_TILE=1 in the environment (read once) forces the per-thread kernel, for A/B tests. */
 int tmf_embed_rgb8(const uint8_t* rgb, uint8_t* out, int n, int h, int w, size_t img_stride,
                    const uint8_t* wm, int wm_shared, double alpha, int block, int mode, void* stream);
 
@@ -134,7 +143,9 @@ int tmf_wm_map_l8(const uint8_t* src, int n, int src_h, int src_w, size_t src_st
  * The per-image loop of the embed page (embed_watermark_page.py:492-558) as one call on
  * HOST memory.  A context owns 3 streams and `depth` device slots on one device; the
  * batch is cut into chunks of ~chunk_bytes (0 = 96 MiB) and H2D copy, fused kernel and D2H
- * copy of successive chunks overlap.  Calls enqueue and return; results are in the host
+ * copy of successive chunks overlap.  Calls enqueue and return (no host-side wait, except when a
+ * device buffer has to grow; if an enqueue fails the context is drained before the error is
+ * returned, so the host buffers are no longer in use); results are in the host
  * buffers after tmf_ctx_synchronize().  For several GPUs: one context per device, split the
  * batch by image, enqueue on all, synchronise each (no collective).  A context is not
  * thread-safe; different contexts are independent.  Host buffers must stay valid until the

@@ -14,40 +14,39 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
-VARIANTS = {          # the last sweeps of round 1 (tables 14-15 of r01_sweep_variants.txt); edit for the next one
+def tile(w, c, s, stash, **kw):
+    d = {"TMF_TILE_WARPS": w, "TMF_TILE_CTAS_PER_SM": c, "TMF_TILE_STAGES": s, "TMF_TILE_STASH": stash}
+    d.update(kw)
+    return d
+
+
+def xtile(w, c, s, **kw):
+    d = {"TMF_XTILE_WARPS": w, "TMF_XTILE_CTAS_PER_SM": c, "TMF_XTILE_STAGES": s}
+    d.update(kw)
+    return d
+
+
+VARIANTS = {          # round 2, fifth sweep: around the new default (16 warps x 1 CTA, single buffer, stash, L2 prefetch)
     "base": {},
-    "c6": {"TMF_EMBED_MIN_CTAS": 6},
-    "c4": {"TMF_EMBED_MIN_CTAS": 4},
-    "biasq": {"TMF_QUANT_DENORM": 0},
-    "stash0": {"TMF_EMBED_STASH": 0},
-    "rp1": {"TMF_EMBED_REPREFETCH": 1},
-    "rowptr": {"TMF_EMBED_ROWPTR": 1},
-    "p2u2": {"TMF_ROW_UNROLL_P2": 2},
-    "x5": {"TMF_FAST_MIN_CTAS": 5},
-    "t128": {"TMF_EMBED_THREADS": 128, "TMF_EXTRACT_THREADS": 128},
-    "persist5": {"TMF_EMBED_PERSIST": 5},
+    "e_split": {"TMF_TILE_SPLIT": 1},
+    "e_p2u2": {"TMF_ROW_UNROLL_P2": 2},
+    "e_p2u8": {"TMF_ROW_UNROLL_P2": 8},
+    "e_u2": {"TMF_ROW_UNROLL": 2, "TMF_ROW_UNROLL_P2": 4},
+    "e_u8": {"TMF_ROW_UNROLL": 8, "TMF_ROW_UNROLL_P2": 4},
+    "pt_notile": {},  # per-thread kernels (run with TMF_NO_TILE=1)
 }
 
 
 def build():
     from thatsmyface_b200 import build as b
     os.makedirs(VDIR, exist_ok=True)
-    items = list(VARIANTS.items())
-    for s in range(0, len(items), 6):
-        procs = []
-        for name, defs in items[s:s + 6]:
-            out = os.path.join(VDIR, f"libtmfwm_{name}.so")
-            cmd = [b._nvcc()] + b.NVCC_FLAGS + ["-Xptxas", "-v"] + [f"-D{k}={v}" for k, v in defs.items()] + \
-                [os.path.join(b.CSRC, src) for src in b.SOURCES] + ["-o", out, "-lcudart"]
-            procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        for name, p in procs:
-            o = p.communicate()[0]
-            regs = []
-            lines = o.splitlines()
-            for i, l in enumerate(lines):
-                if "Compiling entry function" in l and ("embed_fastILi8" in l or "extract_fastILi8" in l or "_tma" in l):
-                    regs.append(" ".join(x.strip() for x in lines[i + 2:i + 4]))
-            print(name, "ok" if p.returncode == 0 else "FAILED\n" + o[-2000:], "|", " || ".join(regs))
+    for name, defs in VARIANTS.items():
+        out = os.path.join(VDIR, f"libtmfwm_{name}.so")
+        try:
+            b.build(defines=[f"{k}={v}" for k, v in defs.items()], out=out)
+            print(name, "ok", flush=True)
+        except RuntimeError as e:
+            print(name, "FAILED", str(e)[-1500:], flush=True)
 
 
 def run_one(images):
@@ -82,6 +81,8 @@ def run(images):
     names = sorted(f[len("libtmfwm_"):-3] for f in os.listdir(VDIR) if f.endswith(".so"))
     for name in names:
         env = dict(os.environ, TMF_LIBPATH=os.path.join(VDIR, f"libtmfwm_{name}.so"))
+        if name.endswith("notile"):
+            env["TMF_NO_TILE"] = "1"
         r = subprocess.run([sys.executable, __file__, "one", str(images)], env=env, capture_output=True, text=True)
         ok = r.returncode == 0 and r.stdout.strip()
         print(name, r.stdout.strip().splitlines()[-1] if ok else "FAILED " + r.stderr[-300:], flush=True)

@@ -24,9 +24,10 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 from thatsmyface_b200 import watermarking as W  # noqa: E402
-from thatsmyface_b200.constants import MODE_FAITHFUL, MODE_FAST  # noqa: E402
+from thatsmyface_b200.constants import MODE_FAITHFUL, MODE_FAST, MODE_LITERAL  # noqa: E402
 
-MODES = [MODE_FAITHFUL, MODE_FAST]
+MODES = [MODE_FAITHFUL, MODE_FAST, MODE_LITERAL]
+BS_MODES = [MODE_FAITHFUL, MODE_FAST]        # the literal product exists for block size 8 only
 ARRAY_CASES = [n for n in golden_names() if not n.startswith(("pil_", "bs"))]
 BS_CASES = [n for n in golden_names() if n.startswith("bs")]
 SIGMA_RTOL = 1e-5
@@ -214,7 +215,7 @@ def test_embed_extract_against_reference_vectors(golden, name, mode):
         assert_extract(ext, g["ref_ext"], f"{name} mode {mode}")
         # cross: the reference's extractor reads the GPU's embedding like its own
         cross = O.extract_array(out, g["rgb"])
-        assert np.abs(cross.astype(int) - g["ref_ext"].astype(int)).max() <= 2
+        assert np.abs(cross.astype(int) - g["ref_ext"].astype(int)).max() <= 1
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -422,42 +423,52 @@ def test_qr_payload_bit_exact_through_the_drop_in_api(mode):
 
 
 # --------------------------------------------------------------------------- the UI's other block sizes
+@pytest.mark.parametrize("mode", BS_MODES)
 @pytest.mark.parametrize("name", BS_CASES)
-def test_other_block_sizes_against_reference_vectors(golden, name):
+def test_other_block_sizes_against_reference_vectors(golden, name, mode):
     g = golden(name)
     bs, alpha = int(g["bs"]), float(g["alpha"])
     x = torch.from_numpy(g["rgb"]).cuda()
-    out = W.embed_tensor(x, torch.from_numpy(g["wm"]).cuda(), alpha, bs).cpu().numpy()
+    out = W.embed_tensor(x, torch.from_numpy(g["wm"]).cuda(), alpha, bs, mode).cpu().numpy()
     assert np.abs(out.astype(int) - g["ref_out"].astype(int)).max() <= 1
-    ext = W.extract_tensor(torch.from_numpy(g["ref_out"]).cuda(), x, alpha, bs).cpu().numpy()
+    ext = W.extract_tensor(torch.from_numpy(g["ref_out"]).cuda(), x, alpha, bs, mode).cpu().numpy()
     assert_extract(ext, g["ref_ext"], name)
-    s = {"block_size": bs, "alpha": alpha}
+    s = {"block_size": bs, "alpha": alpha, "mode": mode}
     pil = W.embed_watermark(Image.fromarray(g["rgb"]), Image.fromarray(g["wm"]), False, s)
     assert np.array_equal(np.array(pil), out)
     e2 = W.extract_watermark(Image.fromarray(g["ref_out"]), Image.fromarray(g["rgb"]), s)
     assert e2.size == (g["wm"].shape[1], g["wm"].shape[0]) and np.array_equal(np.array(e2), ext)
 
 
+def test_literal_mode_is_block_8_only():
+    x = torch.zeros((32, 32, 3), dtype=torch.uint8, device="cuda")
+    m = torch.zeros((2, 2), dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError, match="TMF_MODE_LITERAL"):
+        W.embed_tensor(x, m, 0.1, 16, MODE_LITERAL)
+    assert W.extract_tensor(x, x, 0.1, 16, MODE_LITERAL).shape == (2, 2)     # extract: LITERAL == FAITHFUL
+
+
+@pytest.mark.parametrize("mode", BS_MODES)
 @pytest.mark.parametrize("bs", [4, 6, 10, 12, 14, 16])
-def test_other_block_sizes_vs_oracle(bs):
+def test_other_block_sizes_vs_oracle(bs, mode):
     rng = np.random.default_rng(bs)
     for (h, w) in ((7 * bs + 1, 9 * bs + 3), (16 * bs, 24 * bs)):          # ragged / aligned
         img = natural_like(h, w, bs)
         wm = np.where(rng.random((h // bs, w // bs)) < 0.4, 0, rng.integers(1, 256, (h // bs, w // bs))).astype(np.uint8)
         ref = O.embed_array(img, wm, 0.1, bs)
         x = torch.from_numpy(img).cuda()
-        out = W.embed_tensor(x, torch.from_numpy(wm).cuda(), 0.1, bs).cpu().numpy()
+        out = W.embed_tensor(x, torch.from_numpy(wm).cuda(), 0.1, bs, mode).cpu().numpy()
         assert np.abs(out.astype(int) - ref.astype(int)).max() <= 1, (bs, h, w)
-        assert_extract(W.extract_tensor(torch.from_numpy(ref).cuda(), x, 0.1, bs).cpu().numpy(),
+        assert_extract(W.extract_tensor(torch.from_numpy(ref).cuda(), x, 0.1, bs, mode).cpu().numpy(),
                        O.extract_array(ref, img, 0.1, bs), f"bs {bs}")
-        s0 = W.sigma0_tensor(x, bs).cpu().numpy()
+        s0 = W.sigma0_tensor(x, bs, mode).cpu().numpy()
         Y = O.rgb_to_ycbcr(img)[:, :, 0]
         sref = np.linalg.svd(O.to_blocks(Y, bs).astype(np.float64), compute_uv=False)[..., 0]
         assert (np.abs(s0 - sref) <= SIGMA_RTOL * sref + 1e-12).all()
     # batch path with per-image maps
     imgs = np.stack([natural_like(4 * bs, 6 * bs, k) for k in range(3)])
     wms = rng.integers(0, 256, (3, 4, 6), dtype=np.uint8)
-    got = W.embed_watermark_batch(imgs, wms, 0.1, bs)
+    got = W.embed_watermark_batch(imgs, wms, 0.1, bs, mode)
     for k in range(3):
         assert np.abs(got[k].astype(int) - O.embed_array(imgs[k], wms[k], 0.1, bs).astype(int)).max() <= 1
 

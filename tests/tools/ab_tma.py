@@ -1,15 +1,15 @@
-"""A/B check of the two embed code paths on the same pixels: 16-byte aligned buffers take the
-TMA-staged kernel, the same data at an 8-byte offset takes the per-thread kernel.
+"""A/B check of the two FAST block-8 code paths on the same pixels: 16-byte aligned buffers take
+the TMA-tiled persistent kernels (k_embed_tile / k_extract_tile), the same data at an 8-byte offset
+takes the per-thread kernels.  Outputs must be identical.
 Usage: python tests/tools/ab_tma.py [n] [h] [w]"""
 import os
 import sys
-
-os.environ["TMF_EMBED_TMA"] = "1"      # read once by the library, at its first embed call
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 
 import bench
+from thatsmyface_b200 import _lib
 from thatsmyface_b200 import watermarking as W
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
@@ -28,10 +28,14 @@ off_in = raw_in[8:8 + nbytes].view(n, h, w, 3)
 off_out = raw_out[8:8 + nbytes].view(n, h, w, 3)
 off_in.copy_(imgs)
 assert imgs.data_ptr() % 16 == 0 and off_in.data_ptr() % 16 == 8
+lib = _lib.load()
 for rep in range(3):
     a = W.embed_tensor(imgs, wm, 0.1, 8, 1)
+    path_a = lib.tmf_last_fast_path()
     W.embed_tensor(off_in, wm, 0.1, 8, 1, out=off_out)
+    path_b = lib.tmf_last_fast_path()
     torch.cuda.synchronize()
+    assert (path_a, path_b) == (1, 0), f"expected the tile kernel then the per-thread kernel, got {(path_a, path_b)}"
     d = (a != off_out)
     bad = int(d.sum())
     print(f"rep {rep}: mismatching samples {bad} of {a.numel()}")
@@ -44,3 +48,11 @@ for rep in range(3):
         print("  per image:", per_img)
         rows = d.any(dim=3).any(dim=2).sum(1).tolist()
         print("  rows touched per image:", rows)
+
+# extract: tile kernel (aligned) against the per-thread kernel (offset copies) on the embedded images
+ea = W.extract_tensor(a, imgs, 0.1, 8, 1)
+path_a = lib.tmf_last_fast_path()
+eb = W.extract_tensor(off_out, off_in, 0.1, 8, 1)
+path_b = lib.tmf_last_fast_path()
+torch.cuda.synchronize()
+print(f"extract paths {(path_a, path_b)}: mismatching levels {int((ea != eb).sum())} of {ea.numel()}")

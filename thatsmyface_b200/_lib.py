@@ -17,6 +17,7 @@ PROTOTYPES = {
     "tmf_version": (_i, []),
     "tmf_last_error": (C.c_char_p, []),
     "tmf_device_count": (_i, []),
+    "tmf_last_fast_path": (_i, []),
     "tmf_embed_rgb8": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _i, _d, _i, _i, _vp]),
     "tmf_extract_rgb8": (_i, [_vp, _vp, _vp, _i, _i, _i, _sz, _d, _i, _i, _vp]),
     "tmf_sigma0_rgb8": (_i, [_vp, _vp, _i, _i, _i, _sz, _i, _i, _vp]),

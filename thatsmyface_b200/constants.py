@@ -27,4 +27,5 @@ MAX_WATERMARK_CHARACTERS = DEFAULTS.max_watermark_characters
 
 # `mode` of the fused kernels (include/tmf_wm.h)
 MODE_FAITHFUL = 0   # DCT -> one-sided Jacobi SVD -> IDCT, bit-exact colour
-MODE_FAST = 1       # spatial top-triplet + rank-1 update (default)
+MODE_FAST = 1       # spatial top-triplet + rank-1 update (default); no DCT / SVD executed
+MODE_LITERAL = 2    # block size 8: faithful with the literal U diag(S') V^T product (V accumulated)

@@ -1,0 +1,769 @@
+// FAST mode, block size 8 (tmf_fast.cuh, tmf_rowmath.cuh): two streaming row passes around a
+// certified power iteration on the 8x8 Gram matrix of the block's luma; the block itself is
+// never held in registers.
+//
+//   k_embed_tile / k_extract_tile   persistent kernels fed by the TMA engine: a warp owns a tile
+//       of 32 blocks (two boxes of 16 blocks x 8 image rows); ONE cp.async.bulk.tensor per box
+//       brings it into shared memory, both row passes run out of shared memory, pass 2 writes in
+//       place and ONE cp.async.bulk.tensor per box stores it.  The default wherever the batch is
+//       16-byte aligned and an image row holds a multiple of 16 blocks (512^2, 720p, 1080p, 4K, 8K).
+//   k_embed_fast / k_extract_fast / k_sigma0_fast   one thread per block with per-thread global
+//       accesses: any size, any alignment.
+#include <cuda.h>   // CUtensorMap, cuTensorMapEncodeTiled's prototype (the entry point comes from the runtime)
+
+#include <atomic>
+
+#include "tmf_common.cuh"
+#include "tmf_rowmath.cuh"
+
+namespace tmfi {
+namespace {
+
+constexpr int kRowUnroll = TMF_ROW_UNROLL;
+constexpr int kRowUnrollP2 = TMF_ROW_UNROLL_P2;
+constexpr int kEmbedThreads = TMF_EMBED_THREADS;
+constexpr int kEmbedMinCtas = TMF_EMBED_MIN_CTAS * (128 / TMF_EMBED_THREADS);
+constexpr int kExtractThreads = TMF_EXTRACT_THREADS;
+constexpr int kExtractMinCtas = TMF_FAST_MIN_CTAS * (128 / TMF_EXTRACT_THREADS);
+
+thread_local int g_last_path = 0;
+
+// ---------------------------------------------------------------------------
+// pass 1 over the 8 rows of a block: Gram matrix of its luma (rolled loop: small code).
+// With KEEP, row i's luma is parked in shared memory for pass 2, in a thread-private column
+// (conflict-free): KEEP = 2: four float2 at col[(4i + p) * STRIDE] (the tile kernels: the packed
+// FADD2 results are register PAIRS, two float4 cost 8 MOVs per row to assemble register quads);
+// KEEP = 4: two float4 at col4[(2i + q) * STRIDE] (the per-thread kernel, where the two wider
+// accesses measured 3 % faster than four narrow ones).
+// VEC 8 / 4 / 1: rows in global memory at base + i * pitch; VEC 0: rows of a staged tile in
+// shared memory.
+// ---------------------------------------------------------------------------
+template <int VEC, int KEEP, int STRIDE, typename PITCH>
+__device__ __forceinline__ void gram_of_block(const uint8_t* __restrict__ base0, PITCH pitch, float (&gm)[36],
+                                              float2* __restrict__ col = nullptr) {
+  // uint32_t pitch = a running pointer (one 64-bit add per row; extract / sigma0: +0.5 %);
+  // size_t pitch = base + i * pitch (k_embed_fast, where the running pointer measured 1.7 % slower;
+  // profiles/r01_sweep_variants.txt table 15); VEC 0 = shared memory, constant offsets
+  constexpr bool kRunning = sizeof(PITCH) == 4 && VEC != 0;
+  const uint8_t* __restrict__ base = base0;
+  GramPairs G;
+  gram_clear(G);
+#pragma unroll kRowUnroll
+  for (int i = 0; i < 8; ++i) {
+    uint32_t w[6];
+    float2 y2[4];
+    if (kRunning) { load_row24<VEC>(base, w); base += pitch; }
+    else load_row24<VEC>(base0 + (size_t)i * pitch, w);
+    row_luma2(w, y2);
+    if (KEEP == 2) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) col[(4 * i + p) * STRIDE] = y2[p];
+    } else if (KEEP == 4) {
+      float4* col4 = reinterpret_cast<float4*>(col);
+      col4[(2 * i) * STRIDE] = make_float4(y2[0].x, y2[0].y, y2[1].x, y2[1].y);
+      col4[(2 * i + 1) * STRIDE] = make_float4(y2[2].x, y2[2].y, y2[3].x, y2[3].y);
+    }
+    gram_accumulate_row2(y2, G);
+  }
+  gram_pairs_to_sym(G, gm);
+}
+
+// ---------------------------------------------------------------------------
+// Fused embed, per-thread accesses.
+//
+// Blocks whose watermark value is 0 get d = f32(f64(s0) + alpha*0) - s0 = 0 exactly
+// (watermarking.py:198): their output is the colour round trip alone, so a lane with a zero
+// mark skips pass 1 and the eigenpair.
+// ---------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(kEmbedThreads, kEmbedMinCtas)
+k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGeom g,
+             const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
+  __shared__ float4 lum[16 * kEmbedThreads];      // the block's luma, thread-private column
+  float4* col = lum + threadIdx.x;
+  const long long gb = (long long)blockIdx.x * kEmbedThreads + threadIdx.x;
+  if (gb >= g.total_blocks) return;
+  long long img; int by, bx;
+  uint32_t in_img;
+  const size_t org = block_origin<8>(g, gb, img, by, bx, &in_img);
+  const uint8_t* src = rgb + org;
+  prefetch_block_rows(src, g.pitch32);
+  const uint32_t mark = (uint32_t)__ldg(wm + (wm_shared ? in_img : (uint32_t)gb));   // map index: 32 bits
+  float w[8], f = 0.0f, c = 0.0f;
+  if (mark != 0) {
+    float gm[36];
+    gram_of_block<VEC, 4, kEmbedThreads, size_t>(src, g.row_pitch, gm, reinterpret_cast<float2*>(col));
+    tmf::embed_block_scalars_fast(gm, alpha, mark, w, f, c, nullptr, TMF_LUMA_UNIT);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = 0.0f;
+  }
+  // pass 2: the rows again (L1/L2 hits), rank-1 update, colour out, quantise, store
+  uint8_t* dst = out + org;
+  const float2 w2[4] = {make_float2(w[0], w[1]), make_float2(w[2], w[3]), make_float2(w[4], w[5]), make_float2(w[6], w[7])};
+#pragma unroll kRowUnrollP2
+  for (int i = 0; i < 8; ++i) {
+    uint32_t o[6], wd[6];
+    float4 ya = make_float4(0.f, 0.f, 0.f, 0.f), yb = ya;
+    if (mark != 0) { ya = col[(2 * i) * kEmbedThreads]; yb = col[(2 * i + 1) * kEmbedThreads]; }
+    load_row24<VEC>(src + (size_t)i * g.row_pitch, wd);
+    const float2 y2[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb.x, yb.y), make_float2(yb.z, yb.w)};
+    embed_row_fast2(wd, y2, w2, f, c, o);
+    store_row24<VEC>(dst + (size_t)i * g.row_pitch, o);
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kExtractThreads, kExtractMinCtas)
+k_extract_fast(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ orig, uint8_t* __restrict__ out_wm,
+               BlockGeom g, double alpha) {
+  const long long gb = (long long)blockIdx.x * kExtractThreads + threadIdx.x;
+  if (gb >= g.total_blocks) return;
+  long long img; int by, bx;
+  const size_t org = block_origin<8>(g, gb, img, by, bx);
+  prefetch_block_rows(wmk + org, g.pitch32);
+  prefetch_block_rows(orig + org, g.pitch32);
+  // the two images go through ONE copy of the code (rolled loop): inlining pass 1 and the
+  // eigen-solver twice made the kernel 44 KB and cost ~14 % in instruction-fetch stalls
+  float sw = 0.0f, so = 0.0f;
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    float gm[36];
+    gram_of_block<VEC, 0, 1, uint32_t>((which == 0 ? wmk : orig) + org, g.pitch32, gm);
+    const float sg = tmf::sigma0_from_gram_fast(gm, nullptr, TMF_LUMA_UNIT);
+    if (which == 0) sw = sg; else so = sg;
+  }
+  out_wm[gb] = (uint8_t)tmf::extract_level(sw, so, alpha);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads, TMF_FAST_MIN_CTAS)
+k_sigma0_fast(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, BlockGeom g) {
+  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (gb >= g.total_blocks) return;
+  long long img; int by, bx;
+  const size_t org = block_origin<8>(g, gb, img, by, bx);
+  float gm[36];
+  prefetch_block_rows(rgb + org, g.pitch32);
+  gram_of_block<VEC, 0, 1, uint32_t>(rgb + org, g.pitch32, gm);
+  sigma0[gb] = tmf::sigma0_from_gram_fast(gm, nullptr, TMF_LUMA_UNIT);
+}
+
+// ---------------------------------------------------------------------------
+// TMA-tiled persistent kernels.
+//
+// Why: with per-thread row accesses a warp's 64-bit load covers 256 useful bytes spread over
+// 768, i.e. 6-7 L1 wavefronts instead of 2, three times per row; the resident CTAs' rows do not
+// fit in the L1 left beside the stash, so pass 2 re-reads most rows from L2 (ncu, round 1:
+// 33 M load sectors for 6.2 M of input, L1 hit 58 %, 18 % of the warp samples on long_scoreboard),
+// and every 32-byte output sector reaches L2 in three partial writes.  Round 1's answer, eight
+// per-row cp.async.bulk per warp each way, fixed the memory side and lost on copy-issue
+// instructions (UBLKCP lives on the uniform datapath: a loop per lane).  Here:
+//
+//   * the batch is ONE 3-D tensor (3W/4 words, H rows, N images; strides 3W and img_stride
+//     bytes), and a BOX is 16 blocks x 8 rows = 96 words x 8 rows = 3 KB;
+//   * a warp's TILE is two boxes, consecutive in the linear box order (same block-row, or
+//     wrapping to the next block-row / image): lane L owns block (L & 15) of box (L >> 4), so
+//     no lane idles whenever an image row holds a multiple of 16 blocks;
+//   * lanes 0 and 16 issue ONE cp.async.bulk.tensor.3d each (SASS UTMALDG) onto the warp's
+//     mbarrier; the warp waits, runs pass 1, the eigen-solve and pass 2 out of shared memory
+//     (three conflict-free LDS.64 / STS.64 per row: thread stride 24 B), writing its output
+//     bytes IN PLACE, and the same two lanes issue ONE cp.async.bulk.tensor.3d store each
+//     (UTMASTG): full-line writes, no per-thread STG, no address arithmetic per row;
+//   * the kernel is persistent: a warp walks tiles t, t + W, t + 2W, ... (W = warps in the
+//     grid).  With TMF_TILE_STAGES = 2 a warp has two tile buffers and asks for its NEXT tile
+//     before pass 2 of the current one, so the ~1 us a freshly launched warp used to wait for
+//     its first row is hidden behind its own arithmetic; with 1 it loads, computes, stores in
+//     turn and relies on the other resident warps.
+//   * warps never synchronise with each other: no __syncthreads after the barrier set-up.
+// ---------------------------------------------------------------------------
+constexpr int kBoxBlocks = 16;                        // blocks per box row
+constexpr int kBoxRowBytes = kBoxBlocks * 24;         // 384
+constexpr int kBoxBytes = 8 * kBoxRowBytes;           // 3072
+constexpr int kTileBytes = 2 * kBoxBytes;             // 6144 per warp and stage
+constexpr int kBoxWords = kBoxRowBytes / 4;           // 96: box width in tensor elements (u32)
+
+struct TileGeom {
+  uint32_t total_boxes, total_tiles;
+  uint32_t boxes_per_row, boxes_per_img, nbw, blocks_per_img;
+  FastDiv div_bpi, div_bpr;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "TMF_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra TMF_WAIT_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap* map, uint32_t c0, uint32_t c1, uint32_t c2,
+                                             uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* map, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(src) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_box(const CUtensorMap* map, uint32_t c0, uint32_t c1, uint32_t c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// where a lane's box sits: tensor coordinates of its first element and the map index of the lane's block
+struct BoxAt {
+  uint32_t c0, c1, c2;     // word column, image row, image
+  uint32_t map_idx;        // index of the lane's block in a per-image map (add image * blocks_per_img for per-image maps)
+  bool valid;
+};
+__device__ __forceinline__ BoxAt box_at(const TileGeom& tg, uint32_t box, uint32_t l16) {
+  BoxAt b;
+  b.valid = box < tg.total_boxes;
+  const uint32_t img = fastdiv(box, tg.div_bpi);
+  const uint32_t r = box - img * tg.boxes_per_img;
+  const uint32_t by = fastdiv(r, tg.div_bpr);
+  const uint32_t bxb = r - by * tg.boxes_per_row;
+  b.c0 = bxb * (uint32_t)kBoxWords;
+  b.c1 = by * 8u;
+  b.c2 = img;
+  b.map_idx = by * tg.nbw + bxb * (uint32_t)kBoxBlocks + l16;
+  return b;
+}
+
+template <int WARPS, int STAGES, bool STASH>
+struct EmbedTileSmem {
+  static constexpr int kTiles = WARPS * STAGES * kTileBytes;
+  static constexpr int kStash = STASH ? WARPS * 32 * 32 * 8 : 0;         // 32 float2 per thread
+  static constexpr int kBars = WARPS * STAGES * 8;
+  static constexpr int kTotal = kTiles + kStash + kBars;
+};
+
+template <int WARPS, int CTAS_PER_SM, int STAGES, bool STASH>
+__global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM)
+k_embed_tile(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap dst_map, TileGeom tg,
+             const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
+  using L = EmbedTileSmem<WARPS, STAGES, STASH>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t half = (uint32_t)lane >> 4, l16 = (uint32_t)lane & 15u;
+  const bool leader = l16 == 0;
+  uint8_t* tiles = smem + warp * (STAGES * kTileBytes);
+  const uint32_t tiles_s = smem_u32(tiles);
+  const uint32_t bars = smem_u32(smem + L::kTiles + L::kStash) + warp * (STAGES * 8);
+  float2* col = STASH ? reinterpret_cast<float2*>(smem + L::kTiles) + threadIdx.x : nullptr;
+  constexpr int kStride = WARPS * 32;
+
+  const uint32_t nwarps = gridDim.x * WARPS;
+  uint32_t t = blockIdx.x * WARPS + warp;
+  if (t >= tg.total_tiles) return;                    // whole warp; nothing below is CTA-wide
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(bars + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const uint32_t lane_off = half * kBoxBytes + l16 * 24u;     // this lane's block inside a tile buffer
+  // ask for the first tile
+  BoxAt at = box_at(tg, 2u * t + half, l16);
+  {
+    const uint32_t nb = (2u * t + 1u < tg.total_boxes) ? 2u : 1u;
+    if (lane == 0) mbar_expect_tx(bars, nb * kBoxBytes);
+    __syncwarp();
+    if (leader && at.valid) tma_load_box(tiles_s + half * kBoxBytes, &src_map, at.c0, at.c1, at.c2, bars);
+  }
+  uint32_t mark = 0;
+  if (at.valid) mark = (uint32_t)__ldg(wm + (wm_shared ? 0u : at.c2 * tg.blocks_per_img) + at.map_idx);
+
+  for (uint32_t it = 0;; ++it) {
+    const uint32_t s = (STAGES == 2) ? (it & 1u) : 0u;
+    const uint32_t par = (STAGES == 2) ? ((it >> 1) & 1u) : (it & 1u);
+    uint8_t* mine = tiles + s * kTileBytes + lane_off;
+    const uint32_t tn = t + nwarps;
+    const bool more = tn < tg.total_tiles;
+    BoxAt nx = at;
+    uint32_t mark_n = 0;
+    if (STAGES == 1 && TMF_TILE_L2PF && more) {
+      // single buffer: the next tile cannot be loaded before this one is stored; ask L2 for it now,
+      // so that the load at the end of this iteration finds it there
+      nx = box_at(tg, 2u * tn + half, l16);
+      if (leader && nx.valid) tma_prefetch_box(&src_map, nx.c0, nx.c1, nx.c2);
+    }
+    mbar_wait(bars + 8 * s, par);
+
+    float w[8], f = 0.0f, c = 0.0f;
+    if (at.valid && mark != 0) {
+      float gm[36];
+      gram_of_block<0, STASH ? 2 : 0, kStride, uint32_t>(mine, (uint32_t)kBoxRowBytes, gm, col);
+      tmf::embed_block_scalars_fast(gm, alpha, mark, w, f, c, nullptr, TMF_LUMA_UNIT);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = 0.0f;
+    }
+
+    if (STAGES == 2 && more) {
+      // the other buffer's last store (issued at the end of the previous iteration by these two
+      // lanes) has long been read out; then ask for the next tile: it lands during pass 2
+      nx = box_at(tg, 2u * tn + half, l16);
+      if (leader) bulk_wait_read0();
+      const uint32_t nb = (2u * tn + 1u < tg.total_boxes) ? 2u : 1u;
+      if (lane == 0) mbar_expect_tx(bars + 8 * (s ^ 1u), nb * kBoxBytes);
+      __syncwarp();
+      if (leader && nx.valid)
+        tma_load_box(tiles_s + (s ^ 1u) * kTileBytes + half * kBoxBytes, &src_map, nx.c0, nx.c1, nx.c2, bars + 8 * (s ^ 1u));
+      if (nx.valid) mark_n = (uint32_t)__ldg(wm + (wm_shared ? 0u : nx.c2 * tg.blocks_per_img) + nx.map_idx);
+    }
+
+    if (at.valid) {
+      const float2 w2[4] = {make_float2(w[0], w[1]), make_float2(w[2], w[3]), make_float2(w[4], w[5]), make_float2(w[6], w[7])};
+#pragma unroll kRowUnrollP2
+      for (int i = 0; i < 8; ++i) {
+        uint32_t o[6], wd[6];
+        load_row24<0>(mine + i * kBoxRowBytes, wd);
+        float2 y2[4];
+        if (STASH) {
+#pragma unroll
+          for (int p = 0; p < 4; ++p) y2[p] = col[(4 * i + p) * kStride];     // unmarked lanes: stale values, unused
+        } else {
+          row_luma2(wd, y2);          // the same exact integers pass 1 had: identical results
+        }
+        embed_row_fast2(wd, y2, w2, f, c, o, mark != 0);
+        store_row24<0>(mine + i * kBoxRowBytes, o);
+      }
+    }
+    // generic-proxy writes -> visible to the async proxy, then the two leaders hand their boxes over
+    fence_async_smem();
+    __syncwarp();
+    if (leader && at.valid) {
+      tma_store_box(&dst_map, at.c0, at.c1, at.c2, tiles_s + s * kTileBytes + half * kBoxBytes);
+      bulk_commit();
+    }
+    if (!more) break;
+    if (STAGES == 1) {
+      // single buffer: wait until the store has read it, then refill it
+      if (!TMF_TILE_L2PF) nx = box_at(tg, 2u * tn + half, l16);
+      if (leader) bulk_wait_read0();
+      const uint32_t nb = (2u * tn + 1u < tg.total_boxes) ? 2u : 1u;
+      if (lane == 0) mbar_expect_tx(bars, nb * kBoxBytes);
+      __syncwarp();
+      if (leader && nx.valid) tma_load_box(tiles_s + half * kBoxBytes, &src_map, nx.c0, nx.c1, nx.c2, bars);
+      if (nx.valid) mark_n = (uint32_t)__ldg(wm + (wm_shared ? 0u : nx.c2 * tg.blocks_per_img) + nx.map_idx);
+    }
+    t = tn;
+    at = nx;
+    mark = mark_n;
+  }
+  if (leader) bulk_wait_read0();     // shared memory must outlive the last store's reads
+}
+
+// ---------------------------------------------------------------------------
+// k_embed_tile_split: the single-buffer tile kernel with the buffer handed over in HALVES.
+//
+// A single buffer cannot be refilled before it has been stored, so in k_embed_tile<.., 1, ..> a warp
+// idles from "store issued" to "next tile landed" (ncu: 16 % of its samples sit in the mbarrier
+// wait), and a second buffer does not fit beside the luma stash (6 + 6 + 8 KB per warp = 11 warps
+// per SM).  Here the tile is moved as FOUR boxes of 16 blocks x 4 rows (upper / lower half of each
+// of the two boxes, a tensor map with a 4-row box), each half with its own mbarrier:
+//   pass 2 rows 0-3 done  -> store the upper halves
+//   pass 2 rows 4-5 done  -> the upper store has been read out long ago: load the NEXT tile's
+//                            upper halves (they land while rows 6-7 and the solve's tail run)
+//   pass 2 rows 6-7 done  -> store the lower halves, wait for that read, load the next lower halves
+//   next tile: pass 1 waits for the upper halves (there already), runs rows 0-3, then waits for the
+//   lower halves (in flight since the end of the previous tile; L2-prefetched at its start).
+// Same arithmetic and same results as the other FAST block-8 kernels.
+// ---------------------------------------------------------------------------
+constexpr int kHalfBoxBytes = 4 * kBoxRowBytes;       // 1536
+constexpr int kHalfTileBytes = 2 * kHalfBoxBytes;     // 3072: both boxes' upper (or lower) halves
+
+template <int WARPS>
+struct EmbedSplitSmem {
+  static constexpr int kTiles = WARPS * kTileBytes;
+  static constexpr int kStash = WARPS * 32 * 32 * 8;
+  static constexpr int kBars = WARPS * 2 * 8;
+  static constexpr int kTotal = kTiles + kStash + kBars;
+};
+
+// Gram update from 4 consecutive rows (i0 .. i0+3) of a staged half box
+template <int STRIDE>
+__device__ __forceinline__ void gram_rows4(const uint8_t* __restrict__ rows, int i0, GramPairs& G, float2* __restrict__ col) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t w[6];
+    float2 y2[4];
+    load_row24<0>(rows + i * kBoxRowBytes, w);
+    row_luma2(w, y2);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) col[(4 * (i0 + i) + p) * STRIDE] = y2[p];
+    gram_accumulate_row2(y2, G);
+  }
+}
+
+template <int WARPS, int CTAS_PER_SM>
+__global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM)
+k_embed_tile_split(const __grid_constant__ CUtensorMap src_map8, const __grid_constant__ CUtensorMap src_map4,
+                   const __grid_constant__ CUtensorMap dst_map4, TileGeom tg, const uint8_t* __restrict__ wm,
+                   int wm_shared, double alpha) {
+  using L = EmbedSplitSmem<WARPS>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t half = (uint32_t)lane >> 4, l16 = (uint32_t)lane & 15u;
+  const bool leader = l16 == 0;
+  uint8_t* tiles = smem + warp * kTileBytes;
+  const uint32_t tiles_s = smem_u32(tiles);
+  const uint32_t bars = smem_u32(smem + L::kTiles + L::kStash) + warp * 16;     // [0] upper halves, [8] lower halves
+  float2* col = reinterpret_cast<float2*>(smem + L::kTiles) + threadIdx.x;
+  constexpr int kStride = WARPS * 32;
+
+  const uint32_t nwarps = gridDim.x * WARPS;
+  uint32_t t = blockIdx.x * WARPS + warp;
+  if (t >= tg.total_tiles) return;                    // whole warp; nothing below is CTA-wide
+  if (lane == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  // this lane's block: row r of half h at  mine + h * kHalfTileBytes + r * kBoxRowBytes
+  uint8_t* mine = tiles + half * kHalfBoxBytes + l16 * 24u;
+  const uint32_t box_s = tiles_s + half * kHalfBoxBytes;      // this leader's half box (upper; + kHalfTileBytes = lower)
+
+  auto load_half = [&](uint32_t tile, const BoxAt& b, uint32_t h) {
+    const uint32_t nb = (2u * tile + 1u < tg.total_boxes) ? 2u : 1u;
+    if (lane == 0) mbar_expect_tx(bars + 8 * h, nb * kHalfBoxBytes);
+    __syncwarp();
+    if (leader && b.valid) tma_load_box(box_s + h * kHalfTileBytes, &src_map4, b.c0, b.c1 + 4u * h, b.c2, bars + 8 * h);
+  };
+
+  BoxAt at = box_at(tg, 2u * t + half, l16);
+  load_half(t, at, 0);
+  load_half(t, at, 1);
+  uint32_t mark = 0;
+  if (at.valid) mark = (uint32_t)__ldg(wm + (wm_shared ? 0u : at.c2 * tg.blocks_per_img) + at.map_idx);
+
+  for (uint32_t it = 0;; ++it) {
+    const uint32_t par = it & 1u;
+    const uint32_t tn = t + nwarps;
+    const bool more = tn < tg.total_tiles;
+    BoxAt nx = at;
+    uint32_t mark_n = 0;
+    if (more) {
+      nx = box_at(tg, 2u * tn + half, l16);
+      if (leader && nx.valid) tma_prefetch_box(&src_map8, nx.c0, nx.c1, nx.c2);      // the whole box, into L2
+      if (nx.valid) mark_n = (uint32_t)__ldg(wm + (wm_shared ? 0u : nx.c2 * tg.blocks_per_img) + nx.map_idx);
+    }
+    const bool marked = at.valid && mark != 0;
+
+    // pass 1, half by half
+    GramPairs G;
+    gram_clear(G);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      mbar_wait(bars + 8 * h, par);
+      if (marked) gram_rows4<kStride>(mine + h * kHalfTileBytes, 4 * h, G, col);
+    }
+    float w[8], f = 0.0f, c = 0.0f;
+    if (marked) {
+      float gm[36];
+      gram_pairs_to_sym(G, gm);
+      tmf::embed_block_scalars_fast(gm, alpha, mark, w, f, c, nullptr, TMF_LUMA_UNIT);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = 0.0f;
+    }
+
+    // pass 2, two rows at a time, the halves handed over as they complete
+    const float2 w2[4] = {make_float2(w[0], w[1]), make_float2(w[2], w[3]), make_float2(w[4], w[5]), make_float2(w[6], w[7])};
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      if (at.valid) {
+        uint8_t* rows = mine + (q >> 1) * kHalfTileBytes + (q & 1) * (2 * kBoxRowBytes);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          uint32_t o[6], wd[6];
+          float2 y2[4];
+          load_row24<0>(rows + r * kBoxRowBytes, wd);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) y2[p] = col[(4 * (2 * q + r) + p) * kStride];     // unmarked lanes: stale values, unused
+          embed_row_fast2(wd, y2, w2, f, c, o, mark != 0);
+          store_row24<0>(rows + r * kBoxRowBytes, o);
+        }
+      }
+      if (q == 1 || q == 3) {
+        // generic-proxy writes -> visible to the async proxy, then the two leaders hand their half boxes over
+        const uint32_t h = (uint32_t)q >> 1;
+        fence_async_smem();
+        __syncwarp();
+        if (leader && at.valid) {
+          tma_store_box(&dst_map4, at.c0, at.c1 + 4u * h, at.c2, box_s + h * kHalfTileBytes);
+          bulk_commit();
+        }
+      } else if (q == 2 && more) {
+        if (leader) bulk_wait_read0();              // the upper halves' store (issued two rows ago) has been read out
+        load_half(tn, nx, 0);
+      }
+    }
+    if (!more) break;
+    if (leader) bulk_wait_read0();
+    load_half(tn, nx, 1);
+    t = tn;
+    at = nx;
+    mark = mark_n;
+  }
+  if (leader) bulk_wait_read0();     // shared memory must outlive the last store's reads
+}
+
+// Fused extract, TMA-tiled: the same tile walk over TWO tensors (watermarked, original); a
+// stage holds both tiles (12 KB per warp), pass 1 + eigen-solve run once per image out of
+// shared memory, and the lane writes its one output byte (32 contiguous bytes per warp).
+template <int WARPS, int STAGES>
+struct ExtractTileSmem {
+  static constexpr int kTiles = WARPS * STAGES * 2 * kTileBytes;
+  static constexpr int kBars = WARPS * STAGES * 8;
+  static constexpr int kTotal = kTiles + kBars;
+};
+
+template <int WARPS, int CTAS_PER_SM, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM)
+k_extract_tile(const __grid_constant__ CUtensorMap wmk_map, const __grid_constant__ CUtensorMap orig_map, TileGeom tg,
+               uint8_t* __restrict__ out_wm, double alpha) {
+  using L = ExtractTileSmem<WARPS, STAGES>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t half = (uint32_t)lane >> 4, l16 = (uint32_t)lane & 15u;
+  const bool leader = l16 == 0;
+  uint8_t* tiles = smem + warp * (STAGES * 2 * kTileBytes);
+  const uint32_t tiles_s = smem_u32(tiles);
+  const uint32_t bars = smem_u32(smem + L::kTiles) + warp * (STAGES * 8);
+
+  const uint32_t nwarps = gridDim.x * WARPS;
+  uint32_t t = blockIdx.x * WARPS + warp;
+  if (t >= tg.total_tiles) return;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(bars + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const uint32_t lane_off = half * kBoxBytes + l16 * 24u;
+
+  auto request = [&](uint32_t tile, uint32_t stage, const BoxAt& b) {
+    const uint32_t nb = (2u * tile + 1u < tg.total_boxes) ? 2u : 1u;
+    if (lane == 0) mbar_expect_tx(bars + 8 * stage, 2u * nb * kBoxBytes);
+    __syncwarp();
+    if (leader && b.valid) {
+      const uint32_t dst = tiles_s + stage * (2 * kTileBytes) + half * kBoxBytes;
+      tma_load_box(dst, &wmk_map, b.c0, b.c1, b.c2, bars + 8 * stage);
+      tma_load_box(dst + kTileBytes, &orig_map, b.c0, b.c1, b.c2, bars + 8 * stage);
+    }
+  };
+
+  BoxAt at = box_at(tg, 2u * t + half, l16);
+  request(t, 0, at);
+  if (STAGES == 2 && t + nwarps < tg.total_tiles) request(t + nwarps, 1, box_at(tg, 2u * (t + nwarps) + half, l16));
+
+  for (uint32_t it = 0;; ++it) {
+    const uint32_t s = (STAGES == 2) ? (it & 1u) : 0u;
+    const uint32_t par = (STAGES == 2) ? ((it >> 1) & 1u) : (it & 1u);
+    const uint8_t* mine = tiles + s * (2 * kTileBytes) + lane_off;
+    mbar_wait(bars + 8 * s, par);
+    float sw = 0.0f, so = 0.0f;
+    if (at.valid) {
+#pragma unroll 1
+      for (int which = 0; which < 2; ++which) {
+        float gm[36];
+        gram_of_block<0, 0, 1, uint32_t>(mine + which * kTileBytes, (uint32_t)kBoxRowBytes, gm);
+        const float sg = tmf::sigma0_from_gram_fast(gm, nullptr, TMF_LUMA_UNIT);
+        if (which == 0) sw = sg; else so = sg;
+      }
+      out_wm[at.c2 * tg.blocks_per_img + at.map_idx] = (uint8_t)tmf::extract_level(sw, so, alpha);
+    }
+    // this stage is free again (only generic-proxy reads touched it): refill it with the tile
+    // STAGES steps ahead
+    const uint32_t tn = t + nwarps;
+    if (tn >= tg.total_tiles) break;
+    const uint32_t tr = t + STAGES * nwarps;
+    __syncwarp();                                    // every lane has finished reading the stage
+    if (tr < tg.total_tiles) request(tr, s, box_at(tg, 2u * tr + half, l16));
+    t = tn;
+    at = box_at(tg, 2u * t + half, l16);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static std::atomic<EncodeTiledFn> cached{nullptr};
+  EncodeTiledFn f = cached.load(std::memory_order_acquire);
+  if (f) return f;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess || !p) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  f = reinterpret_cast<EncodeTiledFn>(p);
+  cached.store(f, std::memory_order_release);
+  return f;
+}
+
+// The tile kernels need: block size 8, every image row a multiple of 16 blocks wide... of the
+// part that holds whole blocks; 16-byte aligned base, row pitch and image stride (TMA's rules).
+bool tile_ok(const BlockGeom& g, const void* p0, const void* p1, const void* p2 = nullptr) {
+  static const bool disabled = [] { const char* e = getenv("TMF_NO_TILE"); return e && e[0] == '1'; }();
+  if (disabled) return false;
+  const uintptr_t bits = (uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2 | (uintptr_t)g.img_stride | (uintptr_t)g.row_pitch;
+  return g.bs == 8 && (bits & 15) == 0 && g.nbw >= kBoxBlocks && (g.nbw % kBoxBlocks) == 0 && g.nbh > 0 &&
+         g.img_stride < (1ull << 40);
+}
+
+int make_tile_geom(const BlockGeom& g, TileGeom& tg) {
+  tg.nbw = (uint32_t)g.nbw;
+  tg.blocks_per_img = (uint32_t)g.blocks_per_img;
+  tg.boxes_per_row = (uint32_t)(g.nbw / kBoxBlocks);
+  tg.boxes_per_img = tg.boxes_per_row * (uint32_t)g.nbh;
+  tg.total_boxes = (uint32_t)(g.total_blocks / kBoxBlocks);
+  tg.total_tiles = (tg.total_boxes + 1u) / 2u;
+  tg.div_bpi = make_fastdiv(tg.boxes_per_img);
+  tg.div_bpr = make_fastdiv(tg.boxes_per_row);
+  return TMF_OK;
+}
+
+int make_map(CUtensorMap* m, const void* base, const BlockGeom& g, int n, unsigned box_rows = 8) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(TMF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {(cuuint64_t)(g.row_pitch / 4), (cuuint64_t)g.nbh * 8u, (cuuint64_t)n};
+  const cuuint64_t strides[2] = {(cuuint64_t)g.row_pitch, (cuuint64_t)g.img_stride};
+  const cuuint32_t box[3] = {(cuuint32_t)kBoxWords, box_rows, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TMF_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return TMF_OK;
+}
+
+// opt in to > 48 KB of dynamic shared memory, once per device and kernel (idempotent, thread-safe)
+template <typename K>
+int set_smem(K kernel, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  TMF_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && (done.load(std::memory_order_acquire) >> dev) & 1ull) return TMF_OK;
+  TMF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  TMF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+  return TMF_OK;
+}
+
+}  // namespace
+
+int last_fast_path() { return g_last_path; }
+
+int launch_embed_fast8(const uint8_t* rgb, uint8_t* out, const BlockGeom& g, const uint8_t* wm, int wm_shared,
+                       double alpha, cudaStream_t st) {
+  if (TMF_TILE_SPLIT && tile_ok(g, rgb, out)) {
+    constexpr int W = TMF_TILE_WARPS, C = TMF_TILE_CTAS_PER_SM;
+    auto kernel = k_embed_tile_split<W, C>;
+    constexpr int smem = EmbedSplitSmem<W>::kTotal;
+    static std::atomic<unsigned long long> done{0};
+    if (int rc = set_smem(kernel, smem, done)) return rc;
+    TileGeom tg;
+    make_tile_geom(g, tg);
+    const int n = (int)(g.total_blocks / g.blocks_per_img);
+    CUtensorMap m8, ms, md;
+    if (int rc = make_map(&m8, rgb, g, n, 8)) return rc;
+    if (int rc = make_map(&ms, rgb, g, n, 4)) return rc;
+    if (int rc = make_map(&md, out, g, n, 4)) return rc;
+    const unsigned cap = (unsigned)sm_count() * C;
+    const unsigned need = grid_for(tg.total_tiles, W);
+    kernel<<<need < cap ? need : cap, W * 32, smem, st>>>(m8, ms, md, tg, wm, wm_shared, alpha);
+    g_last_path = 1;
+    return check_launch("embed (tile) kernel launch");
+  }
+  if (tile_ok(g, rgb, out)) {
+    constexpr int W = TMF_TILE_WARPS, C = TMF_TILE_CTAS_PER_SM, S = TMF_TILE_STAGES;
+    constexpr bool STASH = TMF_TILE_STASH != 0;
+    auto kernel = k_embed_tile<W, C, S, STASH>;
+    constexpr int smem = EmbedTileSmem<W, S, STASH>::kTotal;
+    static std::atomic<unsigned long long> done{0};
+    if (int rc = set_smem(kernel, smem, done)) return rc;
+    TileGeom tg;
+    make_tile_geom(g, tg);
+    const int n = (int)(g.total_blocks / g.blocks_per_img);
+    CUtensorMap ms, md;
+    if (int rc = make_map(&ms, rgb, g, n)) return rc;
+    if (int rc = make_map(&md, out, g, n)) return rc;
+    const unsigned cap = (unsigned)sm_count() * C;
+    const unsigned need = grid_for(tg.total_tiles, W);
+    kernel<<<need < cap ? need : cap, W * 32, smem, st>>>(ms, md, tg, wm, wm_shared, alpha);
+    g_last_path = 1;
+    return check_launch("embed (tile) kernel launch");
+  }
+  const unsigned grid = grid_for(g.total_blocks, kEmbedThreads);
+  switch (pick_vec(g, rgb, out)) {
+    case 8: k_embed_fast<8><<<grid, kEmbedThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
+    case 4: k_embed_fast<4><<<grid, kEmbedThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
+    default: k_embed_fast<1><<<grid, kEmbedThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha); break;
+  }
+  g_last_path = 0;
+  return check_launch("embed kernel launch");
+}
+
+int launch_extract_fast8(const uint8_t* wmk, const uint8_t* orig, uint8_t* out_wm, const BlockGeom& g, double alpha,
+                         cudaStream_t st) {
+  if (TMF_XTILE_ENABLE && tile_ok(g, wmk, orig)) {
+    constexpr int W = TMF_XTILE_WARPS, C = TMF_XTILE_CTAS_PER_SM, S = TMF_XTILE_STAGES;
+    auto kernel = k_extract_tile<W, C, S>;
+    constexpr int smem = ExtractTileSmem<W, S>::kTotal;
+    static std::atomic<unsigned long long> done{0};
+    if (int rc = set_smem(kernel, smem, done)) return rc;
+    TileGeom tg;
+    make_tile_geom(g, tg);
+    const int n = (int)(g.total_blocks / g.blocks_per_img);
+    CUtensorMap mw, mo;
+    if (int rc = make_map(&mw, wmk, g, n)) return rc;
+    if (int rc = make_map(&mo, orig, g, n)) return rc;
+    const unsigned cap = (unsigned)sm_count() * C;
+    const unsigned need = grid_for(tg.total_tiles, W);
+    kernel<<<need < cap ? need : cap, W * 32, smem, st>>>(mw, mo, tg, out_wm, alpha);
+    g_last_path = 1;
+    return check_launch("extract (tile) kernel launch");
+  }
+  const unsigned grid = grid_for(g.total_blocks, kExtractThreads);
+  switch (pick_vec(g, wmk, orig)) {
+    case 8: k_extract_fast<8><<<grid, kExtractThreads, 0, st>>>(wmk, orig, out_wm, g, alpha); break;
+    case 4: k_extract_fast<4><<<grid, kExtractThreads, 0, st>>>(wmk, orig, out_wm, g, alpha); break;
+    default: k_extract_fast<1><<<grid, kExtractThreads, 0, st>>>(wmk, orig, out_wm, g, alpha); break;
+  }
+  g_last_path = 0;
+  return check_launch("extract kernel launch");
+}
+
+int launch_sigma0_fast8(const uint8_t* rgb, float* sigma0, const BlockGeom& g, cudaStream_t st) {
+  const unsigned grid = grid_for(g.total_blocks, kThreads);
+  switch (pick_vec(g, rgb, rgb)) {
+    case 8: k_sigma0_fast<8><<<grid, kThreads, 0, st>>>(rgb, sigma0, g); break;
+    case 4: k_sigma0_fast<4><<<grid, kThreads, 0, st>>>(rgb, sigma0, g); break;
+    default: k_sigma0_fast<1><<<grid, kThreads, 0, st>>>(rgb, sigma0, g); break;
+  }
+  return check_launch("sigma0 kernel launch");
+}
+
+}  // namespace tmfi

@@ -1,0 +1,226 @@
+// FAST mode for the other block sizes of the reference's UI (embed_watermark_page.py:324-331:
+// 4..16, even; 8 has its own tuned kernels in fast_kernels.cu).  Same streaming algebra
+// (tmf_fast.cuh is templated on N): pass 1 accumulates the Gram matrix of the block's luma
+// row by row, certified power iteration, pass 2 applies the rank-1 update and the colour
+// round trip.  One thread per block.
+//
+// A block row is 3N bytes = 3N/2 halfwords, held in ceil(3N/4) 32-bit words (w[k] = bytes
+// 4k..4k+3 of the row).  As in the block-8 kernels the luma is the exact integer
+// 299 r + 587 g + 114 b, computed by two IDP.2A per pixel on the packed words (no byte
+// extraction), and pass 2 floors straight onto the integer level with the subnormal
+// quantiser (tmf_rowmath.cuh).
+#include <type_traits>
+
+#include "tmf_common.cuh"
+#include "tmf_rowmath.cuh"
+
+namespace tmfi {
+namespace {
+
+// exact integer luma of pixel j as the magic float 2^23 + (299 r + 587 g + 114 b): two IDP.2A
+template <int NW>
+__device__ __forceinline__ float pixel_luma_magic_n(const uint32_t (&w)[NW], int j) {
+  constexpr uint32_t kRG = 299u | (587u << 16), kB_ = 114u, k_R = 299u << 16, kGB = 587u | (114u << 16);
+  const int k = (3 * j) >> 2;
+  uint32_t m;
+  switch ((3 * j) & 3) {
+    case 0: m = dp2a_hi(w[k], kB_, dp2a_lo(w[k], kRG, 0x4B000000u)); break;
+    case 1: m = dp2a_hi(w[k], kGB, dp2a_lo(w[k], k_R, 0x4B000000u)); break;
+    case 2: m = dp2a_lo(w[k + 1 < NW ? k + 1 : k], kB_, dp2a_hi(w[k], kRG, 0x4B000000u)); break;
+    default: m = dp2a_lo(w[k + 1 < NW ? k + 1 : k], kGB, dp2a_hi(w[k], k_R, 0x4B000000u)); break;
+  }
+  return __uint_as_float(m);
+}
+
+template <int N>
+__device__ __forceinline__ void row_luma_n(const uint32_t (&w)[kRowWords<N>], float (&y)[N]) {
+#pragma unroll
+  for (int p = 0; p < N / 2; ++p) {
+    const float2 v = __fadd2_rn(make_float2(pixel_luma_magic_n<kRowWords<N>>(w, 2 * p),
+                                            pixel_luma_magic_n<kRowWords<N>>(w, 2 * p + 1)), bc2(-8388608.0f));
+    y[2 * p] = v.x; y[2 * p + 1] = v.y;
+  }
+}
+
+// byte B of the row as the subnormal float B * 2^-149 (bit pattern = the byte)
+template <int NW>
+__device__ __forceinline__ float byte_subnormal_n(const uint32_t (&w)[NW], int B) {
+  const uint32_t x = w[B >> 2];
+  const int b = B & 3;
+  uint32_t m;
+  if (b == 3) asm("mad.hi.u32 %0, %1, 256, %2;" : "=r"(m) : "r"(x), "n"(0));
+  else m = __byte_perm(x, 0u, 0x7650u | (uint32_t)b);
+  return __uint_as_float(m);
+}
+
+template <int N, int AL>
+__device__ __forceinline__ void gram_of_block_n(const uint8_t* __restrict__ base, size_t pitch, float* gm) {
+#pragma unroll
+  for (int k = 0; k < N * (N + 1) / 2; ++k) gm[k] = 0.0f;
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) {
+    uint32_t w[kRowWords<N>];
+    float y[N];
+    load_row_n<N, AL>(base + (size_t)i * pitch, w);
+    row_luma_n<N>(w, y);
+    tmf::gram_accumulate_row<N>(y, gm);
+  }
+}
+
+// pass 2 for one row: same arithmetic as embed_row_fast2 (tmf_rowmath.cuh) for any even N
+template <int N>
+__device__ __forceinline__ void embed_row_n(const uint32_t (&w)[kRowWords<N>], const float (&wv)[N], float f, float c,
+                                            bool marked, uint32_t (&o)[kRowWords<N>]) {
+  constexpr int NW = kRowWords<N>;
+  float du = c;
+  if (marked) {
+    float y[N];
+    row_luma_n<N>(w, y);
+    du = fmaf(f, tmf::dotn<N>(y, wv), c);
+  }
+  du *= 1.7763568394002505e-15f;   // 2^-49
+  int q[4 * NW];
+#pragma unroll
+  for (int k = 3 * N; k < 4 * NW; ++k) q[k] = 0;
+  constexpr float k2p100 = 1.2676506002282294e30f, k2m100 = 7.888609052210118e-31f;
+#pragma unroll
+  for (int p = 0; p < N / 2; ++p) {
+    const int B = 6 * p;
+    const float2 d2 = __fmul2_rn(bc2(du), make_float2(wv[2 * p], wv[2 * p + 1]));
+    const float2 mr = make_float2(byte_subnormal_n<NW>(w, B), byte_subnormal_n<NW>(w, B + 3));
+    const float2 mg = make_float2(byte_subnormal_n<NW>(w, B + 1), byte_subnormal_n<NW>(w, B + 4));
+    const float2 mb = make_float2(byte_subnormal_n<NW>(w, B + 2), byte_subnormal_n<NW>(w, B + 5));
+    const float2 u = __ffma2_rn(mg, bc2(-1.0f), mr), v = __ffma2_rn(mg, bc2(-1.0f), mb);
+    const float2 sR = __ffma2_rn(bc2(5.00e-4f * k2p100), u, __ffma2_rn(bc2(3.57e-4f * k2p100), v, d2));
+    const float2 sG = __ffma2_rn(bc2(1.36e-4f * k2p100), u, __ffma2_rn(bc2(-1.66e-4f * k2p100), v, d2));
+    const float2 sB = __ffma2_rn(bc2(-6.37e-4f * k2p100), u, __ffma2_rn(bc2(5.00e-4f * k2p100), v, d2));
+    const float2 tR = __ffma2_rd(sR, bc2(k2m100), mr), tG = __ffma2_rd(sG, bc2(k2m100), mg),
+                 tB = __ffma2_rd(sB, bc2(k2m100), mb);
+    q[B] = __float_as_int(tR.x); q[B + 1] = __float_as_int(tG.x); q[B + 2] = __float_as_int(tB.x);
+    q[B + 3] = __float_as_int(tR.y); q[B + 4] = __float_as_int(tG.y); q[B + 5] = __float_as_int(tB.y);
+  }
+#pragma unroll
+  for (int k = 0; k < NW; ++k) o[k] = tmf::pack4_sat_u8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
+}
+
+template <int N> __host__ __device__ constexpr int fastn_min_ctas() { return N <= 6 ? 6 : (N <= 10 ? 4 : 3); }
+
+template <int N, int AL>
+__global__ void __launch_bounds__(kThreads, fastn_min_ctas<N>())
+k_embed_fast_n(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGeom g,
+               const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
+  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (gb >= g.total_blocks) return;
+  long long img; int by, bx;
+  uint32_t in_img;
+  const size_t org = block_origin<N>(g, gb, img, by, bx, &in_img);
+  const uint8_t* src = rgb + org;
+  uint8_t* dst = out + org;
+  prefetch_block_rows<N>(src, g.pitch32);
+  const uint32_t mark = (uint32_t)__ldg(wm + (wm_shared ? in_img : (uint32_t)gb));
+  float w[N], f = 0.0f, c = 0.0f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) w[i] = 0.0f;
+  if (mark != 0) {
+    float gm[N * (N + 1) / 2];
+    gram_of_block_n<N, AL>(src, g.row_pitch, gm);
+    tmf::embed_block_scalars_fast<N>(gm, alpha, mark, w, f, c, nullptr, TMF_LUMA_UNIT);
+  }
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) {
+    uint32_t wd[kRowWords<N>], o[kRowWords<N>];
+    load_row_n<N, AL>(src + (size_t)i * g.row_pitch, wd);
+    embed_row_n<N>(wd, w, f, c, mark != 0, o);
+    store_row_n<N, AL>(dst + (size_t)i * g.row_pitch, o);
+  }
+}
+
+template <int N, int AL>
+__device__ __forceinline__ float sigma0_of_block_n(const uint8_t* __restrict__ base, size_t pitch) {
+  float gm[N * (N + 1) / 2];
+  gram_of_block_n<N, AL>(base, pitch, gm);
+  return tmf::sigma0_from_gram_fast<N>(gm, nullptr, TMF_LUMA_UNIT);
+}
+
+template <int N, int AL>
+__global__ void __launch_bounds__(kThreads, fastn_min_ctas<N>())
+k_extract_fast_n(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ orig, uint8_t* __restrict__ out_wm,
+                 BlockGeom g, double alpha) {
+  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (gb >= g.total_blocks) return;
+  long long img; int by, bx;
+  const size_t org = block_origin<N>(g, gb, img, by, bx);
+  prefetch_block_rows<N>(wmk + org, g.pitch32);
+  prefetch_block_rows<N>(orig + org, g.pitch32);
+  float sw = 0.0f, so = 0.0f;
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {          // one copy of the code for both images
+    const float sg = sigma0_of_block_n<N, AL>((which == 0 ? wmk : orig) + org, g.row_pitch);
+    if (which == 0) sw = sg; else so = sg;
+  }
+  out_wm[gb] = (uint8_t)tmf::extract_level(sw, so, alpha);
+}
+
+template <int N, int AL>
+__global__ void __launch_bounds__(kThreads, fastn_min_ctas<N>())
+k_sigma0_fast_n(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, BlockGeom g) {
+  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (gb >= g.total_blocks) return;
+  long long img; int by, bx;
+  const size_t org = block_origin<N>(g, gb, img, by, bx);
+  sigma0[gb] = sigma0_of_block_n<N, AL>(rgb + org, g.row_pitch);
+}
+
+// Dispatch over the block sizes other than 8.  f(N, A) gets integral constants: N = block size,
+// A = access width the block rows allow (4 needs 3N % 4 == 0 || the trailing halfword: any even N
+// has 3N % 2 == 0, so rows that start 4-byte aligned can use word loads plus one halfword).
+template <int N, typename F>
+void with_access_width(int al, F&& f) {
+  // block rows start at multiples of 3N bytes from a 4-byte aligned row start: 4-byte aligned
+  // for every block only when 3N % 4 == 0
+  if (al == 4 && (3 * N) % 4 == 0) f(std::integral_constant<int, N>{}, std::integral_constant<int, 4>{});
+  else if (al >= 2) f(std::integral_constant<int, N>{}, std::integral_constant<int, 2>{});
+  else f(std::integral_constant<int, N>{}, std::integral_constant<int, 1>{});
+}
+template <typename F>
+void for_block_size(int n, int al, F&& f) {
+  switch (n) {
+    case 4: with_access_width<4>(al, f); break;
+    case 6: with_access_width<6>(al, f); break;
+    case 10: with_access_width<10>(al, f); break;
+    case 12: with_access_width<12>(al, f); break;
+    case 14: with_access_width<14>(al, f); break;
+    case 16: with_access_width<16>(al, f); break;
+    default: break;
+  }
+}
+
+}  // namespace
+
+int launch_embed_fast_n(const uint8_t* rgb, uint8_t* out, const BlockGeom& g, const uint8_t* wm, int wm_shared,
+                        double alpha, cudaStream_t st) {
+  const unsigned grid = grid_for(g.total_blocks, kThreads);
+  for_block_size(g.bs, row_alignment(g, rgb, out), [&](auto n_, auto a_) {
+    k_embed_fast_n<decltype(n_)::value, decltype(a_)::value><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha);
+  });
+  return check_launch("embed kernel launch");
+}
+
+int launch_extract_fast_n(const uint8_t* wmk, const uint8_t* orig, uint8_t* out_wm, const BlockGeom& g, double alpha,
+                          cudaStream_t st) {
+  const unsigned grid = grid_for(g.total_blocks, kThreads);
+  for_block_size(g.bs, row_alignment(g, wmk, orig), [&](auto n_, auto a_) {
+    k_extract_fast_n<decltype(n_)::value, decltype(a_)::value><<<grid, kThreads, 0, st>>>(wmk, orig, out_wm, g, alpha);
+  });
+  return check_launch("extract kernel launch");
+}
+
+int launch_sigma0_fast_n(const uint8_t* rgb, float* sigma0, const BlockGeom& g, cudaStream_t st) {
+  const unsigned grid = grid_for(g.total_blocks, kThreads);
+  for_block_size(g.bs, row_alignment(g, rgb, rgb), [&](auto n_, auto a_) {
+    k_sigma0_fast_n<decltype(n_)::value, decltype(a_)::value><<<grid, kThreads, 0, st>>>(rgb, sigma0, g);
+  });
+  return check_launch("sigma0 kernel launch");
+}
+
+}  // namespace tmfi

@@ -543,6 +543,46 @@ TMF_HD float embed_block_faithful(float* a, float* v, double alpha, uint32_t wm_
   return sig;
 }
 
+// Faithful pipeline up to the top singular triplet, without accumulating V:
+// DCT -> one-sided Jacobi (values-only form: A <- A V = U diag(sigma)) -> the top column is
+// sigma_top * u0, so u0 needs no V; the right vector follows from the block itself,
+// v0 = D^T u0 / sigma_top, and the reference's U diag(S') V^T = D + d u0 v0^T exactly
+// (watermarking.py:198-201 changes S[0] only).  Carried back to the spatial domain by the
+// orthonormal DCT: block' = B + d (C^T u0)(C^T v0)^T with C^T v0 = B^T (C^T u0) / sigma_top.
+// a[64] = the luma block (destroyed); uB[8] <- C^T u0 (unit norm).  Returns sigma_top in the
+// block's units (0 for an all-zero block: then uB is the constant 1/sqrt(8) vector, which with
+// v = uB reproduces LAPACK's U = V = I convention - the mark lands on the DC coefficient).
+TMF_HD float top_left_vector_faithful(float* a, float* uB, int* sweeps) {
+  dct8x8(a);
+  float unscale;
+  const int sw = jacobi_svd8<false>(a, nullptr, unscale);
+  if (sweeps) *sweeps = sw;
+  float n2[8];
+  column_norms2(a, n2);
+  float best = n2[0];
+  int top = 0;
+#pragma unroll
+  for (int j = 1; j < 8; ++j) {
+    if (n2[j] > best) { best = n2[j]; top = j; }
+  }
+  const float nrm = f_sqrt(best);
+  if (!(nrm > 0.0f)) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) uB[i] = TMF_G0;
+    return 0.0f;
+  }
+  const float inv = f_div(1.0f, nrm);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float u = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u = (j == top) ? a[8 * i + j] : u;
+    uB[i] = u * inv;
+  }
+  idct8<1>(uB);
+  return nrm * unscale;
+}
+
 // Largest singular value of the DCT of one luma block (extract side).
 TMF_HD float sigma0_block_faithful(float* a, int* sweeps) {
   dct8x8(a);

@@ -1,0 +1,73 @@
+// Launch-shape knobs of the fused kernels - the ONLY compile-time tunables of the library.
+// profiles/sweep_variants.py rebuilds the library with -D overrides of these and times the
+// alternatives on the GPU; the defaults below are the measured winners
+// (profiles/r01_sweep_variants.txt, profiles/r02_sweep_variants.txt).  Every knob whose sweep
+// verdict was "loses" has been deleted together with its code path; the tables are the record.
+#pragma once
+
+// rows per iteration of the rolled row loops of the per-thread fast kernels (1, 2, 4, 8)
+#ifndef TMF_ROW_UNROLL
+#define TMF_ROW_UNROLL 4
+#endif
+#ifndef TMF_ROW_UNROLL_P2
+#define TMF_ROW_UNROLL_P2 TMF_ROW_UNROLL   // the embed kernels' pass 2, separately
+#endif
+
+// per-thread fast kernels (k_embed_fast / k_extract_fast / k_sigma0_fast): CTA size and the
+// __launch_bounds__ minimum CTAs per SM, given per 128 threads
+#ifndef TMF_EMBED_THREADS
+#define TMF_EMBED_THREADS 32     // one-warp CTAs give registers and stash back as soon as their warp ends
+#endif
+#ifndef TMF_EMBED_MIN_CTAS
+#define TMF_EMBED_MIN_CTAS 5     // 96 registers: no spill; 160 KB of stash leave 60 KB of L1
+#endif
+#ifndef TMF_EXTRACT_THREADS
+#define TMF_EXTRACT_THREADS 32
+#endif
+#ifndef TMF_FAST_MIN_CTAS
+#define TMF_FAST_MIN_CTAS 6      // extract / sigma0: 80 registers
+#endif
+
+// TMA-tiled persistent embed kernel (k_embed_tile): warps per CTA, CTAs per SM, smem stages per
+// warp (1 = load / compute / store in turn, 2 = the next tile's load in flight during pass 2),
+// and whether pass 1 parks the luma in shared memory (1) or pass 2 recomputes it (0)
+#ifndef TMF_TILE_WARPS
+#define TMF_TILE_WARPS 16
+#endif
+#ifndef TMF_TILE_CTAS_PER_SM
+#define TMF_TILE_CTAS_PER_SM 1
+#endif
+#ifndef TMF_TILE_STAGES
+#define TMF_TILE_STAGES 1
+#endif
+#ifndef TMF_TILE_STASH
+#define TMF_TILE_STASH 1
+#endif
+#ifndef TMF_TILE_SPLIT
+#define TMF_TILE_SPLIT 0         // 1: k_embed_tile_split (single buffer + stash, handed over in halves)
+#endif
+#ifndef TMF_TILE_L2PF
+#define TMF_TILE_L2PF 1          // single-stage tiles: L2 prefetch of the warp's next tile at the start of this one
+#endif
+// the same for the TMA-tiled extract kernel (k_extract_tile; it has no stash)
+#ifndef TMF_XTILE_WARPS
+#define TMF_XTILE_WARPS 4
+#endif
+#ifndef TMF_XTILE_CTAS_PER_SM
+#define TMF_XTILE_CTAS_PER_SM 4
+#endif
+#ifndef TMF_XTILE_STAGES
+#define TMF_XTILE_STAGES 1
+#endif
+#ifndef TMF_XTILE_ENABLE
+#define TMF_XTILE_ENABLE 0       // 0: extract always takes the per-thread kernel
+#endif
+
+// faithful kernels, block size 8: minimum CTAs of 128 threads per SM - the literal form (A and V
+// in registers) and the default form / extract / sigma0 (A only)
+#ifndef TMF_FAITHFUL_MIN_CTAS
+#define TMF_FAITHFUL_MIN_CTAS 3
+#endif
+#ifndef TMF_FAITHFUL_R1_MIN_CTAS
+#define TMF_FAITHFUL_R1_MIN_CTAS 4
+#endif

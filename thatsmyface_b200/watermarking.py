@@ -38,7 +38,7 @@ import numpy as np
 from PIL import Image
 
 from . import _lib
-from .constants import ALPHA, BLOCK_SIZE, MODE_FAITHFUL, MODE_FAST
+from .constants import ALPHA, BLOCK_SIZE, MODE_FAITHFUL, MODE_FAST, MODE_LITERAL  # noqa: F401
 
 __all__ = [
     "get_watermark_settings", "rgb_to_ycbcr", "ycbcr_to_rgb", "apply_dct_to_block",

@@ -26,14 +26,11 @@ def xtile(w, c, s, **kw):
     return d
 
 
-VARIANTS = {          # round 2, fifth sweep: around the new default (16 warps x 1 CTA, single buffer, stash, L2 prefetch)
+VARIANTS = {          # round 2, sixth sweep: faithful kernels (run with TMF_SWEEP_MODE=0): CTAs per SM of the V-free form
     "base": {},
-    "e_split": {"TMF_TILE_SPLIT": 1},
-    "e_p2u2": {"TMF_ROW_UNROLL_P2": 2},
-    "e_p2u8": {"TMF_ROW_UNROLL_P2": 8},
-    "e_u2": {"TMF_ROW_UNROLL": 2, "TMF_ROW_UNROLL_P2": 4},
-    "e_u8": {"TMF_ROW_UNROLL": 8, "TMF_ROW_UNROLL_P2": 4},
-    "pt_notile": {},  # per-thread kernels (run with TMF_NO_TILE=1)
+    "f_c3": {"TMF_FAITHFUL_R1_MIN_CTAS": 3},
+    "f_c5": {"TMF_FAITHFUL_R1_MIN_CTAS": 5},
+    "f_c6": {"TMF_FAITHFUL_R1_MIN_CTAS": 6},
 }
 
 

@@ -257,7 +257,7 @@ __device__ __forceinline__ float jacobi_smem(float* __restrict__ m) {
         }
       }
     }
-    if (!(worst > TMF_JACOBI_DONE)) break;
+    if (!(worst > TMF_JACOBI_MORE)) break;
   }
   return unscale;
 }

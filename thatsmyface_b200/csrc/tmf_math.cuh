@@ -54,6 +54,13 @@ TMF_HD double d_mul(double a, double b) {
   volatile double r = a * b; return r;
 #endif
 }
+TMF_HD double d_add(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(a, b);
+#else
+  volatile double r = a + b; return r;
+#endif
+}
 TMF_HD double d_div(double a, double b) {
 #if defined(__CUDA_ARCH__)
   return __ddiv_rn(a, b);
@@ -117,7 +124,13 @@ TMF_HD float dot3_npdot(double t0, double t1, double t2, float x0, float x1, flo
 // reciprocal step (checked for every byte by tests/test_hostsim.py and by the
 // bit-exact colour taps), which avoids the ~12-instruction division sequence.
 TMF_HD float unit_from_u8(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  // the byte as a float through the 2^23 magic number (one logic op + one FADD on the full-rate
+  // pipes; I2F runs at 16 lanes/clk/SM, profiles/r01_ubench.txt) - exact for 0..255
+  const float k = __uint_as_float(v | 0x4B000000u) - 8388608.0f;
+#else
   const float k = (float)v;
+#endif
   const float r = 0.00392156885936856270f;        // RN32(1/255)
   const float q0 = f_mul(k, r);
   const float e = fmaf(-q0, 255.0f, k);           // exact residual
@@ -137,15 +150,28 @@ TMF_HD void chroma_exact(float r, float g, float b, float& cb, float& cr) {
 // float32, truncation toward zero.
 TMF_HD void ycc_to_rgb8_exact(float y, float cb, float cr, uint32_t& R, uint32_t& G, uint32_t& B) {
   float zb = f_add(cb, -0.5f), zr = f_add(cr, -0.5f);
-  float r = dot3_npdot(1.0, 0.0, 1.403, y, zb, zr);
-  float g = dot3_npdot(1.0, -0.344, -0.714, y, zb, zr);
-  float b = dot3_npdot(1.0, 1.773, 0.0, y, zb, zr);
+  // np.dot rows (1, 0, 1.403), (1, -0.344, -0.714), (1, 1.773, 0) in dot3_npdot's order
+  // acc = t1 x1; acc = fma(t0, x0, acc); acc = fma(t2, x2, acc), with the exact steps folded:
+  // 0 * zb = +-0 and fma(1, y, +-0) = y; fma(1, y, acc) = y + acc; fma(0, zr, acc) = acc
+  // (identical bits for finite inputs; a NaN / Inf input is garbage in the reference too)
+  const double yd = (double)y, zbd = (double)zb, zrd = (double)zr;
+  float r = (float)d_fma(1.403, zrd, yd);
+  float g = (float)d_fma(-0.714, zrd, d_add(yd, d_mul(-0.344, zbd)));
+  float b = (float)d_add(yd, d_mul(1.773, zbd));
   r = fminf(fmaxf(r, 0.0f), 1.0f);
   g = fminf(fmaxf(g, 0.0f), 1.0f);
   b = fminf(fmaxf(b, 0.0f), 1.0f);
+#if defined(__CUDA_ARCH__)
+  // 0 <= x <= 255: truncation == floor, taken with one FADD.RM onto 1.5 * 2^23 and an integer
+  // subtraction instead of F2I (16 lanes/clk/SM)
+  R = (uint32_t)(__float_as_int(__fadd_rd(f_mul(r, 255.0f), 12582912.0f)) - 0x4B400000);
+  G = (uint32_t)(__float_as_int(__fadd_rd(f_mul(g, 255.0f), 12582912.0f)) - 0x4B400000);
+  B = (uint32_t)(__float_as_int(__fadd_rd(f_mul(b, 255.0f), 12582912.0f)) - 0x4B400000);
+#else
   R = (uint32_t)f_mul(r, 255.0f);
   G = (uint32_t)f_mul(g, 255.0f);
   B = (uint32_t)f_mul(b, 255.0f);
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -230,6 +256,8 @@ TMF_HD void idct8x8(float* a) {
 #define TMF_JACOBI_F32X2 1             // packed-fp32 rounds on the device (0: scalar rounds)
 #endif
 #define TMF_JACOBI_TOL 1.0e-6f
+#define TMF_JACOBI_DONE 3.0e-4f        // see the stop rule below
+#define TMF_JACOBI_MORE 1.5f          // jacobi_cs returned 2 for some pair of the sweep
 #define TMF_JACOBI_FLOOR 1.0e-14f      // (eps * ||A||_F)^2 with ||A||_F ~ 1
 #define TMF_JACOBI_MAX_SWEEPS 12
 
@@ -256,16 +284,17 @@ TMF_HD float pow2_scale_for(float frob2, float& unscale) {
 #endif
 }
 
-// Rotation of one column pair from its Gram entries (al, be, ga).  Returns the
-// |cosine| between the two columns if the pair is rotated (c, s set), else 0
-// with (c, s) = (1, 0).  Branch-free: every lane runs the same instructions.
+// Rotation of one column pair from its Gram entries (al, be, ga).  Returns 0 if the pair is
+// left alone ((c, s) = (1, 0)), 1 if it is rotated, 2 if it is rotated and its |cosine| was
+// above TMF_JACOBI_DONE (another sweep is needed).  The cosine tests are done on squares,
+// ga^2 against tol^2 al be: no division, no square root.  Branch-free.
 TMF_HD float jacobi_cs(float al, float be, float ga, float& c, float& s) {
   const float ab = al * be;
-  const float rab = f_rsqrt(ab);                       // inf when ab == 0 (then rot is false)
-  const float cosv = fabsf(ga) * rab;
-  const bool rot = (cosv > TMF_JACOBI_TOL) && (fminf(al, be) > TMF_JACOBI_FLOOR);
+  const float gg = ga * ga;
+  const float g2 = ga + ga;
+  const bool rot = (gg > (TMF_JACOBI_TOL * TMF_JACOBI_TOL) * ab) && (fminf(al, be) > TMF_JACOBI_FLOOR);
   // tan of the rotation angle, smaller root: t = 2g / (d + sign(d) sqrt(d^2 + 4g^2))
-  const float d = be - al, g2 = ga + ga;
+  const float d = be - al;
   const float r = f_sqrt_fast(fmaf(g2, g2, d * d));
   const float t = g2 * f_rcp_fast(d + copysignf(r, d));
   const float tt = fmaf(t, t, 1.0f);
@@ -273,7 +302,7 @@ TMF_HD float jacobi_cs(float al, float be, float ga, float& c, float& s) {
   cc = fmaf(0.5f * cc, fmaf(-tt * cc, cc, 1.0f), cc);  // one Newton step: c^2 + s^2 = 1 to ~1 ulp
   c = rot ? cc : 1.0f;
   s = rot ? cc * t : 0.0f;
-  return rot ? cosv : 0.0f;
+  return rot ? ((gg > (TMF_JACOBI_DONE * TMF_JACOBI_DONE) * ab) ? 2.0f : 1.0f) : 0.0f;
 }
 
 // Round-robin ("chess tournament") ordering.  A round rotates the disjoint
@@ -403,7 +432,6 @@ __device__ __forceinline__ float jacobi_round2(float2* a2, float2* v2, float* n2
 // TMF_JACOBI_DONE: Jacobi converges quadratically, so the sweep that just ran
 // leaves cosines of order DONE^2 - no extra sweep is spent only to find out
 // that nothing rotates.
-#define TMF_JACOBI_DONE 3.0e-4f
 
 template <bool WITH_V>
 TMF_HD int jacobi_svd8(float* a, float* v, float& unscale) {
@@ -440,7 +468,7 @@ TMF_HD int jacobi_svd8(float* a, float* v, float& unscale) {
 #pragma unroll 1
     for (int r = 0; r < 7; ++r) worst = fmaxf(worst, jacobi_round2<WITH_V>(a2, v2, n2));
     sweeps += (worst > 0.0f) ? 1 : 0;
-    more = worst > TMF_JACOBI_DONE;
+    more = worst > TMF_JACOBI_MORE;
   }
 #pragma unroll
   for (int rp = 0; rp < 4; ++rp)
@@ -457,7 +485,7 @@ TMF_HD int jacobi_svd8(float* a, float* v, float& unscale) {
 #endif
     for (int r = 0; r < 7; ++r) worst = fmaxf(worst, jacobi_round<WITH_V>(a, v));
     sweeps += (worst > 0.0f) ? 1 : 0;
-    more = worst > TMF_JACOBI_DONE;
+    more = worst > TMF_JACOBI_MORE;
   }
 #endif
   return sweeps;

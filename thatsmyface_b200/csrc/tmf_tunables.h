@@ -7,10 +7,10 @@
 
 // rows per iteration of the rolled row loops of the per-thread fast kernels (1, 2, 4, 8)
 #ifndef TMF_ROW_UNROLL
-#define TMF_ROW_UNROLL 4
+#define TMF_ROW_UNROLL 8
 #endif
 #ifndef TMF_ROW_UNROLL_P2
-#define TMF_ROW_UNROLL_P2 TMF_ROW_UNROLL   // the embed kernels' pass 2, separately
+#define TMF_ROW_UNROLL_P2 4                // the embed kernels' pass 2, separately
 #endif
 
 // per-thread fast kernels (k_embed_fast / k_extract_fast / k_sigma0_fast): CTA size and the
@@ -69,5 +69,5 @@
 #define TMF_FAITHFUL_MIN_CTAS 3
 #endif
 #ifndef TMF_FAITHFUL_R1_MIN_CTAS
-#define TMF_FAITHFUL_R1_MIN_CTAS 4
+#define TMF_FAITHFUL_R1_MIN_CTAS 3
 #endif

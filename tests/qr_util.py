@@ -46,13 +46,25 @@ def qr_png(payload: bytes, size: int = 1000) -> bytes:
     return buf.getvalue()
 
 
-def decode_map(level_map: np.ndarray):
-    """qrcode_to_text on an extracted (H//8, W//8) map: threshold, 4x nearest upscale
-    (SURVEY.md 8(f) rank 4), detect + decode, base64 -> bytes.  None if undecodable."""
-    img = np.where(level_map >= 128, 255, 0).astype(np.uint8)
-    img = np.kron(img, np.ones((4, 4), np.uint8))
-    img = np.pad(img, 16, constant_values=255)
-    txt, _, _ = cv2.QRCodeDetector().detectAndDecode(img)
+def decode_map(level_map: np.ndarray, scales=(4, 6, 3, 8)):
+    """qrcode_to_text on an extracted (H//8, W//8) map: threshold, nearest upscale (SURVEY.md 8(f)
+    rank 4; OpenCV's detector is sensitive to the module size in pixels, so a few integer factors
+    are tried in turn), detect + decode, base64 -> bytes.  None if undecodable."""
+    binary = np.where(level_map >= 128, 255, 0).astype(np.uint8)
+    for sc in scales:
+        img = np.pad(np.kron(binary, np.ones((sc, sc), np.uint8)), 16, constant_values=255)
+        txt, _, _ = cv2.QRCodeDetector().detectAndDecode(img)
+        if txt:
+            try:
+                return base64.b64decode(txt)
+            except Exception:
+                return None
+    return None
+
+
+def decode_prepared(img):
+    """qrcode_to_text on an image that is already decodable (``prepare_for_decoding``'s output)."""
+    txt, _, _ = cv2.QRCodeDetector().detectAndDecode(np.asarray(img.convert("L")))
     if not txt:
         return None
     try:

@@ -25,10 +25,15 @@ def test_reference_arm_prints_one_json_line_with_contract_keys():
               "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "MP/s" and d["value"] > 0 and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    from oracle import live_reference
+    assert d["cpu_baseline"]["kind"] == ("reference" if live_reference.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"] and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["metric"] == bench.METRIC and "workload" in d["config"]
+    # both arms print the same `config` object (the driver compares them)
+    import argparse
+    assert d["config"] == bench.make_config(argparse.Namespace(images=1024), 1)
 
 
 def test_reference_arm_other_ranks_stay_silent():
@@ -40,9 +45,13 @@ def test_reference_arm_other_ranks_stay_silent():
 
 def test_synthetic_workload_helpers():
     wm = bench.make_wm_map()
-    assert wm.shape == (135, 240) and wm.dtype == np.uint8 and set(np.unique(wm)) == {0, 255}
-    assert (wm[:, :58] == 255).all() and (wm[:6] == 255).all()          # white padding around the QR-like core
+    assert wm.shape == (135, 240) and wm.dtype == np.uint8 and wm.min() == 0 and wm.max() == 255
+    assert (wm[:, :52] == 255).all() and (wm[:, -52:] == 255).all()     # white padding left and right of the centred QR
+    assert 0.2 < (wm < 128).mean() < 0.35                               # a QR: about half of its modules are dark
     assert np.array_equal(wm, bench.make_wm_map())
+    import qr_util as Q
+    payload, _ = bench.payload_and_png()
+    assert Q.decode_map(wm) == payload                                  # the map itself carries the payload
     kinds = [bench.image_kind(i) for i in range(8)]
     assert kinds.count("natural") == 4 and kinds.count("random") == 2 and kinds.count("regions") == 2
     a = bench.cpu_image(5, 64)
@@ -63,7 +72,7 @@ def test_clock_sampler_parses_nvidia_smi_rows():
 @pytest.mark.gpu
 def test_b200_arm_prints_one_json_line_with_contract_keys():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--steps", "3", "--warmup", "3",
-                        "--images", "32", "--e2e-images", "8", "--no-cpu-baseline"],
+                        "--images", "32", "--no-cpu-baseline", "--sustain-seconds", "0.2"],
                        capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -76,6 +85,17 @@ def test_b200_arm_prints_one_json_line_with_contract_keys():
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-3
     e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] >= 8 * 1080 * 1920 * 3 and e["d2h_bytes_per_step"] == 8 * 1080 * 1920 * 3
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] >= 32 * 1080 * 1920 * 3 and e["d2h_bytes_per_step"] == 32 * 1080 * 1920 * 3
+    assert e["images_per_step_per_gpu"] == 32                      # the e2e leg runs on the same shard as `value`
     assert e["matches_device_path"] is True and d["extract"]["watermark_bits_recovered_on_natural_images"] is True
+    assert e["extract"]["value"] > 0 and e["extract"]["h2d_bytes_per_step"] == 2 * 32 * 1080 * 1920 * 3
+    assert e["extract"]["matches_device_path"] is True
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert rf["sustained"]["frac"] > 0 and rf["faithful"]["embed_frac"] > 0 and rf["extract"]["frac"] > 0
+    c = d["configs"]
+    assert set(c) >= {"c1_512_embed_extract", "c2_4k_latency", "c4_extract_with_helper_data", "c5_svd_sweep", "block_sizes"}
+    assert all("error" not in (v if isinstance(v, dict) else {}) for v in c.values()), c
+    assert c["c1_512_embed_extract"]["payload_decoded_gpu"] is True and c["c2_4k_latency"]["payload_byte_exact"] is True
+    nat = c["c4_extract_with_helper_data"]["payload_byte_exact"]["natural"].split("/")
+    assert nat[0] == nat[1] and int(nat[1]) == 16
+    assert c["c4_extract_with_helper_data"]["helper_data"]["decrypted_text_equals_input"] is True

@@ -247,10 +247,26 @@ def test_pil_api_drop_in(golden, name, mode):
 
 
 # --------------------------------------------------------------------------- seeded inputs vs the oracle
-@pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("kind,shape", [("random", (256, 384)), ("natural", (264, 328)), ("regions", (256, 256)),
-                                        ("gray", (128, 136)), ("natural", (203, 187)), ("natural", (100, 100))])
-def test_embed_extract_vs_oracle(kind, shape, mode):
+ORACLE_CASES = [("random", (256, 384)), ("natural", (264, 328)), ("regions", (256, 256)), ("gray", (128, 136)),
+                ("natural", (203, 187)), ("natural", (100, 100))]
+
+# Largest fraction of SAMPLES that may differ (by 1 LSB) from the reference, per content kind and mode.
+# SURVEY.md 8(c) states 1e-3 for ordinary content; the campaign split by mode (tests/tools/parity_campaign.py,
+# profiles/r02_parity_campaign_by_mode.json: random 6e-5, natural 3e-4 in FAST and FAITHFUL alike, 2e-4 / 8e-4
+# with the literal product) shows what is behind the numbers: on grey pixels (R = G = B) and flat regions the
+# reference's own value sits exactly on an integer and its LAPACK / pocketfft round-off decides the LSB, so about
+# one sample in ten differs there in EVERY mode, the one with bit-exact colour included - inherent to a
+# truncating quantiser, not an implementation gap ("Parity contract").
+MAX_DIFFERING = {
+    ("random", MODE_FAST): 1e-3, ("random", MODE_FAITHFUL): 1e-3, ("random", MODE_LITERAL): 1e-3,
+    ("natural", MODE_FAST): 1e-3, ("natural", MODE_FAITHFUL): 1e-3, ("natural", MODE_LITERAL): 2.5e-3,
+    # measured on these seeded cases (tests/tools/case_fractions.py): regions 0.191 / 0.191 / 0.047, grey 0.293 / 0.293 / 0.283
+    ("regions", MODE_FAST): 0.25, ("regions", MODE_FAITHFUL): 0.25, ("regions", MODE_LITERAL): 0.10,
+    ("gray", MODE_FAST): 0.35, ("gray", MODE_FAITHFUL): 0.35, ("gray", MODE_LITERAL): 0.35,
+}
+
+
+def oracle_case(kind, shape):
     h, w = shape
     rng = np.random.default_rng(h * 1000 + w)
     if kind == "random":
@@ -263,12 +279,18 @@ def test_embed_extract_vs_oracle(kind, shape, mode):
         rgb = np.repeat(natural_like(h, w, 9)[:, :, 1:2], 3, axis=2)
     wm = np.where(rng.random((h // 8, w // 8)) < 0.5, 0, 255).astype(np.uint8)
     wm[0, :] = rng.integers(0, 256, w // 8)      # some grey levels too
+    return rgb, wm
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("kind,shape", ORACLE_CASES)
+def test_embed_extract_vs_oracle(kind, shape, mode):
+    rgb, wm = oracle_case(kind, shape)
     taps = {}
     ref = O.embed_array(rgb, wm, taps=taps)
     out = gpu_embed(rgb, wm, mode=mode)
     frac = assert_pixels(out, ref, taps["S"], f"{kind}{shape} mode {mode}")
-    if kind in ("random", "natural"):
-        assert frac <= 2e-3, f"{frac:.2e} of samples differ"     # expected ~1e-4 .. 4e-4
+    assert frac <= MAX_DIFFERING[(kind, mode)], f"{kind} mode {mode}: {frac:.2e} of samples differ"
     assert_extract(gpu_extract(ref, rgb, mode=mode), O.extract_array(ref, rgb), f"{kind}{shape}")
     # GPU end to end: the bits that went in come out
     ext = gpu_extract(out, rgb, mode=mode)
@@ -342,7 +364,11 @@ def test_errors_are_loud_and_typed():
     with pytest.raises(ValueError, match="same shape"):
         W.extract_tensor(x, torch.zeros((24, 16, 3), dtype=torch.uint8, device="cuda"))
     with pytest.raises(ValueError, match="same size"):
-        W.extract_watermark(Image.new("RGB", (16, 16)), Image.new("RGB", (24, 16)))
+        W.extract_watermark(Image.new("RGB", (24, 16)), Image.new("RGB", (16, 16)))
+    # a LARGER original works as in the reference (its top-left region is read, watermarking.py:254-276)
+    big = Image.fromarray(natural_like(24, 40, 3))
+    small = big.crop((0, 0, 32, 16))
+    assert np.array_equal(np.array(W.extract_watermark(small, big)), np.array(W.extract_watermark(small, small)))
     with pytest.raises(ValueError):
         W.embed_tensor(x.float(), m)
 

@@ -1,6 +1,7 @@
-"""(Under tests/: the oracle is the checker.)  Randomised parity campaign on the GPU box: many small images of mixed content, both
-modes, several alphas and block sizes, CUDA path (through the C ABI) vs the oracle.
-Prints one JSON summary.  python tests/tools/parity_campaign.py [images_per_kind]"""
+"""(Under tests/: the oracle is the checker.)  Randomised parity campaign on the GPU box: many small images of mixed content,
+every mode (fast, faithful; literal too at block size 8), several alphas and block sizes, CUDA path (through the C ABI) vs
+the oracle.  Prints one JSON summary with the differing fraction split by content kind AND mode.
+python tests/tools/parity_campaign.py [images_per_kind]"""
 import json
 import os
 import sys
@@ -43,9 +44,12 @@ def main(per_kind):
     rng = np.random.default_rng(2026)
     kinds = ("random", "natural", "gray", "dark", "sat", "edges")
     res = {"images": 0, "max_pixel_diff_outside_ties": 0, "max_extract_diff": 0, "bit_mismatches_decided": 0,
-           "tie_blocks_excluded": 0, "blocks": 0, "worst": None, "by_kind": {}}
+           "tie_blocks_excluded": 0, "blocks": 0, "worst": None, "by_kind": {}, "by_kind_and_mode": {}}
+    mode_names = {0: "faithful", 1: "fast", 2: "literal"}
     for kind in kinds:
         agg = {"n": 0, "frac_px_differing": [], "max_px": 0, "max_ext": 0}
+        per_mode = {m: {"pixels": 0, "pixels_differing": 0, "samples": 0, "samples_differing": 0, "ext": 0, "ext_differing": 0}
+                    for m in mode_names}
         for k in range(per_kind):
             bs = 8 if k % 4 else int(rng.choice([4, 6, 10, 12, 14, 16]))
             h, w = int(rng.integers(2, 20)) * bs + int(rng.integers(0, bs)), int(rng.integers(2, 24)) * bs + int(rng.integers(0, bs))
@@ -63,10 +67,11 @@ def main(per_kind):
             t = np.repeat(np.repeat(tie, bs, 0), bs, 1)
             tie_px[: t.shape[0], : t.shape[1]] = t
             x = torch.from_numpy(img).cuda()
-            for mode in ((0, 1) if bs == 8 else (1,)):
+            for mode in ((0, 1, 2) if bs == 8 else (0, 1)):
                 out = W.embed_tensor(x, torch.from_numpy(wm).cuda(), alpha, bs, mode).cpu().numpy()
-                d = np.abs(out.astype(int) - ref.astype(int)).max(axis=2)
-                d[tie_px] = 0
+                d3 = np.abs(out.astype(int) - ref.astype(int))
+                d3[tie_px] = 0
+                d = d3.max(axis=2)
                 ext = W.extract_tensor(torch.from_numpy(ref).cuda(), x, alpha, bs, mode).cpu().numpy()
                 de = np.abs(ext.astype(int) - ref_ext.astype(int))
                 decided = np.abs(ref_ext.astype(int) - 128) > 1
@@ -74,6 +79,10 @@ def main(per_kind):
                 agg["max_px"] = max(agg["max_px"], int(d.max()))
                 agg["max_ext"] = max(agg["max_ext"], int(de.max()) if de.size else 0)
                 agg["frac_px_differing"].append(float((d > 0).mean()))
+                pm = per_mode[mode]
+                pm["pixels"] += d.size; pm["pixels_differing"] += int((d > 0).sum())
+                pm["samples"] += d3.size; pm["samples_differing"] += int((d3 > 0).sum())
+                pm["ext"] += de.size; pm["ext_differing"] += int((de > 0).sum())
                 res["bit_mismatches_decided"] += bad_bits
                 if d.max() > 1 or (de.size and de.max() > 1) or bad_bits:
                     res["worst"] = {"kind": kind, "k": k, "bs": bs, "alpha": alpha, "mode": mode, "shape": [h, w],
@@ -84,6 +93,11 @@ def main(per_kind):
             res["tie_blocks_excluded"] += int(tie.sum())
         res["by_kind"][kind] = {"n": agg["n"], "max_pixel_diff": agg["max_px"], "max_extract_diff": agg["max_ext"],
                                 "mean_fraction_of_pixels_differing_by_1": round(float(np.mean(agg["frac_px_differing"])), 6)}
+        res["by_kind_and_mode"][kind] = {
+            mode_names[m]: {"fraction_of_pixels_differing_by_1": round(v["pixels_differing"] / max(v["pixels"], 1), 6),
+                            "fraction_of_samples_differing_by_1": round(v["samples_differing"] / max(v["samples"], 1), 6),
+                            "fraction_of_extracted_levels_differing_by_1": round(v["ext_differing"] / max(v["ext"], 1), 6)}
+            for m, v in per_mode.items()}
         res["max_pixel_diff_outside_ties"] = max(res["max_pixel_diff_outside_ties"], agg["max_px"])
         res["max_extract_diff"] = max(res["max_extract_diff"], agg["max_ext"])
     print(json.dumps(res, indent=1))

@@ -168,26 +168,40 @@ def run_batch(kind, a, b, wm_map, alpha=ALPHA, block_size=BLOCK_SIZE, mode=None,
     if out is None:
         tout = torch.empty(out_shape, dtype=torch.uint8, pin_memory=ta.is_pinned())
     else:
+        contiguous = out.flags["C_CONTIGUOUS"] if isinstance(out, np.ndarray) else \
+            (isinstance(out, torch.Tensor) and out.is_contiguous())
+        if not contiguous:      # a contiguous copy would receive the results and the caller's buffer would stay untouched
+            raise ValueError("out must be C-contiguous")
         tout, _ = _as_cpu_u8(out, "out")
         if tuple(tout.shape) != out_shape:
             raise ValueError(f"out must have shape {out_shape}")
 
     img_bytes, out_bytes, map_bytes = h * w * 3, int(np.prod(out_shape[1:])), nbh * nbw
+    # every context is resolved before anything is queued (a bad device id fails here, with nothing in flight)
+    plan = [(context_for(dev, chunk_bytes, depth), lo, hi)
+            for dev, (lo, hi) in zip(devices, shard_ranges(n, len(devices))) if hi > lo]
     ctxs = []
-    for dev, (lo, hi) in zip(devices, shard_ranges(n, len(devices))):
-        if hi <= lo:
-            continue
-        ctx = context_for(dev, chunk_bytes, depth)
-        if stats is not None:
-            ctx.stats(reset=True)
-        src = ta.data_ptr() + lo * img_bytes
-        dst = tout.data_ptr() + lo * out_bytes
-        if kind == "embed":
-            wm_ptr = tw.data_ptr() + (0 if shared else lo * map_bytes)
-            ctx.embed_async(src, dst, hi - lo, h, w, wm_ptr, shared, alpha, block_size, mode)
-        else:
-            ctx.extract_async(src, tb.data_ptr() + lo * img_bytes, dst, hi - lo, h, w, alpha, block_size, mode)
-        ctxs.append(ctx)
+    try:
+        for ctx, lo, hi in plan:
+            if stats is not None:
+                ctx.stats(reset=True)
+            src = ta.data_ptr() + lo * img_bytes
+            dst = tout.data_ptr() + lo * out_bytes
+            ctxs.append(ctx)
+            if kind == "embed":
+                wm_ptr = tw.data_ptr() + (0 if shared else lo * map_bytes)
+                ctx.embed_async(src, dst, hi - lo, h, w, wm_ptr, shared, alpha, block_size, mode)
+            else:
+                ctx.extract_async(src, tb.data_ptr() + lo * img_bytes, dst, hi - lo, h, w, alpha, block_size, mode)
+    except BaseException:
+        # an enqueue failed (out of device memory, ...): the contexts queued so far still copy from / into
+        # ta, tb, tw and tout - join them before those buffers can be released, then re-raise
+        for ctx in ctxs:
+            try:
+                ctx.synchronize()
+            except Exception:
+                pass
+        raise
     for ctx in ctxs:       # every device has its work queued before the first wait
         ctx.synchronize()
     if stats is not None:

@@ -588,9 +588,15 @@ def _stage_acquire(size, pin=True):
 
 
 def _stage_release(st):
-    """Back to the pool (its pending H2D, if any, is waited for by the next ``fill``)."""
+    """Back to the pool (its pending H2D, if any, is waited for by the next ``fill``).  A block that
+    leaves the pool instead - too large to keep, or evicted - is unpinned and freed, so its pending
+    copy is waited for first: the DMA must never read freed host memory."""
     global _stage_free_bytes
     dropped = []
+    if st.view.nbytes > _STAGE_POOL_BYTES:       # never pooled: it would evict itself at once
+        if st.event is not None:
+            st.event.synchronize()
+        return
     with _stage_lock:
         size = (st.view.shape[1], st.view.shape[0])
         _stage_free.setdefault(size, []).append(st)
@@ -603,7 +609,10 @@ def _stage_release(st):
             if not lst:
                 del _stage_free[old_size]
             dropped.append(victim)
-    del dropped                                                 # unpinned outside the lock
+    for victim in dropped:                                      # waited for and unpinned outside the lock
+        if victim.event is not None:
+            victim.event.synchronize()
+    del dropped
 
 
 def _rgbx_array_to_pil(arr4):
@@ -643,7 +652,9 @@ def _pil_to_device_rgb(image):
 
 
 def _device_rgb_to_pil(t):
-    """CUDA uint8 (H, W, 3) tensor -> new mode-"RGB" PIL image (Image.fromarray(...), watermarking.py:219)."""
+    """CUDA uint8 (H, W, 3) tensor -> new mode-"RGB" PIL image (Image.fromarray(...), watermarking.py:219).
+    The unpacked pixels cross PCIe into a pooled page-locked staging block (a pageable destination goes
+    through the driver's bounce buffers at a few GB/s); the image the caller keeps is one PIL copy of it."""
     torch = _torch()
     if not _fast_pil() or t.numel() == 0:
         return _array_to_pil(t.cpu().numpy(), "RGB")
@@ -651,7 +662,21 @@ def _device_rgb_to_pil(t):
     t = t.contiguous()
     dev4 = torch.empty((h, w, 4), dtype=torch.uint8, device=t.device)
     _lib.check(_lib.load().tmf_rgb8_to_rgbx8(t.data_ptr(), dev4.data_ptr(), h * w, 255, _stream_ptr(torch)))
-    return _rgbx_array_to_pil(dev4.cpu().numpy())
+    st = _stage_acquire((w, h))
+    try:
+        if st.event is not None:
+            st.event.synchronize()                             # a previous H2D out of this block
+            st.event = None
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)       # the Arrow view is read-only to NumPy; the block is ours
+            host = torch.from_numpy(st.view)
+        host.copy_(dev4, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return st.img.copy()                                   # fresh image owning its memory; releases the GIL
+    finally:
+        _stage_release(st)
 
 
 def embed_watermark(image, watermark_data, preserve_ratio=False, custom_settings=None):
@@ -676,9 +701,13 @@ def extract_watermark(watermarked_image, original_image, custom_settings=None):
     block_size, alpha, mode = _resolve(custom_settings)
     _require_supported_block(block_size)
     if watermarked_image.size != original_image.size:
+        # the reference takes the block grid from the watermarked image (:254-256) and indexes the
+        # original with it (:272-276): a larger original works there - its top-left region is read
         (wa, ha), (wb, hb) = watermarked_image.size, original_image.size
-        raise ValueError(f"watermarked image {wa}x{ha} and original image "
-                         f"{wb}x{hb} must have the same size")
+        if wb < wa or hb < ha:
+            raise ValueError(f"watermarked image {wa}x{ha} and original image {wb}x{hb} must have the same size "
+                             "(or the original must be at least as large)")
+        original_image = original_image.crop((0, 0, wa, ha))
     a = _pil_to_device_rgb(watermarked_image)
     b = _pil_to_device_rgb(original_image)
     out = extract_tensor(a, b, alpha, block_size, mode)

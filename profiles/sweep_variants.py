@@ -26,11 +26,11 @@ def xtile(w, c, s, **kw):
     return d
 
 
-VARIANTS = {          # round 2, sixth sweep: faithful kernels (run with TMF_SWEEP_MODE=0): CTAs per SM of the V-free form
+VARIANTS = {          # round 2, seventh sweep: occupancy of the generic-N fast kernels (run profiles/block_size_sweep.py per variant)
     "base": {},
-    "f_c3": {"TMF_FAITHFUL_R1_MIN_CTAS": 3},
-    "f_c5": {"TMF_FAITHFUL_R1_MIN_CTAS": 5},
-    "f_c6": {"TMF_FAITHFUL_R1_MIN_CTAS": 6},
+    "n_large2": {"TMF_FASTN_CTAS_LARGE": 2},
+    "n_12c2_10c3": {"TMF_FASTN_CTAS_12": 2, "TMF_FASTN_CTAS_10": 3},
+    "n_12c4_10c5": {"TMF_FASTN_CTAS_12": 4, "TMF_FASTN_CTAS_10": 5, "TMF_FASTN_CTAS_LARGE": 4},
 }
 
 

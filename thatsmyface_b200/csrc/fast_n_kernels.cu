@@ -9,6 +9,16 @@
 // 299 r + 587 g + 114 b, computed by two IDP.2A per pixel on the packed words (no byte
 // extraction), and pass 2 floors straight onto the integer level with the subnormal
 // quantiser (tmf_rowmath.cuh).
+//
+// Access width AL.  4: block rows start 4-byte aligned (3N % 4 == 0: N = 4, 12, 16).  3: sizes with
+// 3N % 4 == 2 (N = 6, 10, 14) in rows that start 4-byte aligned: blocks alternate between offsets
+// 0 and 2 (mod 4) along a row, so every lane reads the aligned words that cover its row and
+// funnel-shifts by 0 or 16 bits, and writes aligned words too - the one word an even block shares
+// with its right-hand neighbour is completed with a shuffle and written by the even lane
+// (2-byte stores cost 16 partial writes per 32-byte sector: bs 10 embed 132k -> 441k MP/s,
+// bs 6 300k -> 593k).  The two bytes an even block reads past its end belong to the next block or
+// to the W % N strip: 3N % 4 == 2 with 4-byte rows and no strip implies an even block count per row.
+// 2 / 1: halfword / byte accesses for everything else.
 #include <type_traits>
 
 #include "tmf_common.cuh"
@@ -16,6 +26,48 @@
 
 namespace tmfi {
 namespace {
+
+// ---- row I/O: AL = 3 is the aligned-words-with-parity path, the others are tmf_common.cuh's ----
+template <int N, int AL>
+__device__ __forceinline__ void load_row(const uint8_t* __restrict__ p, bool odd, uint32_t (&w)[kRowWords<N>]) {
+  if (AL == 3) {
+    constexpr int NW = kRowWords<N>;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p - (odd ? 2 : 0));
+    const uint32_t sh = odd ? 16u : 0u;
+    uint32_t r[NW];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) r[k] = __ldg(q + k);
+#pragma unroll
+    for (int k = 0; k < NW - 1; ++k) w[k] = __funnelshift_r(r[k], r[k + 1], sh);
+    w[NW - 1] = r[NW - 1] >> sh;          // even lanes: the upper half is the neighbour's (never used)
+  } else {
+    load_row_n<N, (AL == 3 ? 2 : AL)>(p, w);
+  }
+}
+
+template <int N, int AL>
+__device__ __forceinline__ void store_row(uint8_t* __restrict__ p, bool odd, bool paired, const uint32_t (&o)[kRowWords<N>]) {
+  if (AL == 3) {
+    constexpr int NW = kRowWords<N>;
+    // The word an even block shares with its right-hand neighbour is completed with a shuffle and
+    // written by the even lane.  `paired`: that neighbour is the next lane (same warp, same row) for an
+    // even block / the previous lane for an odd one; an unpaired lane (lane 31, lane 0, the last block
+    // of a row with an odd block count) writes its own halfword instead.
+    const uint32_t nb = __shfl_down_sync(__activemask(), o[0], 1);
+    uint32_t* q = reinterpret_cast<uint32_t*>(p + (odd ? 2 : 0));
+    const uint32_t sh = odd ? 16u : 0u;
+#pragma unroll
+    for (int k = 0; k < NW - 1; ++k) q[k] = __funnelshift_r(o[k], o[k + 1], sh);
+    if (!odd) {
+      if (paired) q[NW - 1] = (o[NW - 1] & 0xffffu) | (nb << 16);
+      else *reinterpret_cast<uint16_t*>(p + 4 * (NW - 1)) = (uint16_t)o[NW - 1];
+    } else if (!paired) {
+      *reinterpret_cast<uint16_t*>(p) = (uint16_t)o[0];
+    }
+  } else {
+    store_row_n<N, (AL == 3 ? 2 : AL)>(p, o);
+  }
+}
 
 // exact integer luma of pixel j as the magic float 2^23 + (299 r + 587 g + 114 b): two IDP.2A
 template <int NW>
@@ -54,14 +106,14 @@ __device__ __forceinline__ float byte_subnormal_n(const uint32_t (&w)[NW], int B
 }
 
 template <int N, int AL>
-__device__ __forceinline__ void gram_of_block_n(const uint8_t* __restrict__ base, size_t pitch, float* gm) {
+__device__ __forceinline__ void gram_of_block_n(const uint8_t* __restrict__ base, size_t pitch, bool odd, float* gm) {
 #pragma unroll
   for (int k = 0; k < N * (N + 1) / 2; ++k) gm[k] = 0.0f;
 #pragma unroll 1
   for (int i = 0; i < N; ++i) {
     uint32_t w[kRowWords<N>];
     float y[N];
-    load_row_n<N, AL>(base + (size_t)i * pitch, w);
+    load_row<N, AL>(base + (size_t)i * pitch, odd, w);
     row_luma_n<N>(w, y);
     tmf::gram_accumulate_row<N>(y, gm);
   }
@@ -103,7 +155,9 @@ __device__ __forceinline__ void embed_row_n(const uint32_t (&w)[kRowWords<N>], c
   for (int k = 0; k < NW; ++k) o[k] = tmf::pack4_sat_u8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
 }
 
-template <int N> __host__ __device__ constexpr int fastn_min_ctas() { return N <= 6 ? 6 : (N <= 10 ? 4 : 3); }
+template <int N> __host__ __device__ constexpr int fastn_min_ctas() {
+  return N <= 6 ? TMF_FASTN_CTAS_SMALL : (N <= 10 ? TMF_FASTN_CTAS_10 : (N <= 12 ? TMF_FASTN_CTAS_12 : TMF_FASTN_CTAS_LARGE));
+}
 
 template <int N, int AL>
 __global__ void __launch_bounds__(kThreads, fastn_min_ctas<N>())
@@ -118,27 +172,30 @@ k_embed_fast_n(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, Block
   uint8_t* dst = out + org;
   prefetch_block_rows<N>(src, g.pitch32);
   const uint32_t mark = (uint32_t)__ldg(wm + (wm_shared ? in_img : (uint32_t)gb));
+  const bool odd = (bx & 1) != 0;
+  const int lane = threadIdx.x & 31;
+  const bool paired = odd ? lane > 0 : (lane < 31 && bx + 1 < g.nbw && gb + 1 < g.total_blocks);
   float w[N], f = 0.0f, c = 0.0f;
 #pragma unroll
   for (int i = 0; i < N; ++i) w[i] = 0.0f;
   if (mark != 0) {
     float gm[N * (N + 1) / 2];
-    gram_of_block_n<N, AL>(src, g.row_pitch, gm);
+    gram_of_block_n<N, AL>(src, g.row_pitch, odd, gm);
     tmf::embed_block_scalars_fast<N>(gm, alpha, mark, w, f, c, nullptr, TMF_LUMA_UNIT);
   }
 #pragma unroll 1
   for (int i = 0; i < N; ++i) {
     uint32_t wd[kRowWords<N>], o[kRowWords<N>];
-    load_row_n<N, AL>(src + (size_t)i * g.row_pitch, wd);
+    load_row<N, AL>(src + (size_t)i * g.row_pitch, odd, wd);
     embed_row_n<N>(wd, w, f, c, mark != 0, o);
-    store_row_n<N, AL>(dst + (size_t)i * g.row_pitch, o);
+    store_row<N, AL>(dst + (size_t)i * g.row_pitch, odd, paired, o);
   }
 }
 
 template <int N, int AL>
-__device__ __forceinline__ float sigma0_of_block_n(const uint8_t* __restrict__ base, size_t pitch) {
+__device__ __forceinline__ float sigma0_of_block_n(const uint8_t* __restrict__ base, size_t pitch, bool odd) {
   float gm[N * (N + 1) / 2];
-  gram_of_block_n<N, AL>(base, pitch, gm);
+  gram_of_block_n<N, AL>(base, pitch, odd, gm);
   return tmf::sigma0_from_gram_fast<N>(gm, nullptr, TMF_LUMA_UNIT);
 }
 
@@ -155,7 +212,7 @@ k_extract_fast_n(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ or
   float sw = 0.0f, so = 0.0f;
 #pragma unroll 1
   for (int which = 0; which < 2; ++which) {          // one copy of the code for both images
-    const float sg = sigma0_of_block_n<N, AL>((which == 0 ? wmk : orig) + org, g.row_pitch);
+    const float sg = sigma0_of_block_n<N, AL>((which == 0 ? wmk : orig) + org, g.row_pitch, (bx & 1) != 0);
     if (which == 0) sw = sg; else so = sg;
   }
   out_wm[gb] = (uint8_t)tmf::extract_level(sw, so, alpha);
@@ -168,29 +225,29 @@ k_sigma0_fast_n(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, Blo
   if (gb >= g.total_blocks) return;
   long long img; int by, bx;
   const size_t org = block_origin<N>(g, gb, img, by, bx);
-  sigma0[gb] = sigma0_of_block_n<N, AL>(rgb + org, g.row_pitch);
+  sigma0[gb] = sigma0_of_block_n<N, AL>(rgb + org, g.row_pitch, (bx & 1) != 0);
 }
 
 // Dispatch over the block sizes other than 8.  f(N, A) gets integral constants: N = block size,
 // A = access width the block rows allow (4 needs 3N % 4 == 0 || the trailing halfword: any even N
 // has 3N % 2 == 0, so rows that start 4-byte aligned can use word loads plus one halfword).
 template <int N, typename F>
-void with_access_width(int al, F&& f) {
-  // block rows start at multiples of 3N bytes from a 4-byte aligned row start: 4-byte aligned
-  // for every block only when 3N % 4 == 0
+void with_access_width(int al, bool, F&& f) {
   if (al == 4 && (3 * N) % 4 == 0) f(std::integral_constant<int, N>{}, std::integral_constant<int, 4>{});
+  else if (al == 4) f(std::integral_constant<int, N>{}, std::integral_constant<int, 3>{});
   else if (al >= 2) f(std::integral_constant<int, N>{}, std::integral_constant<int, 2>{});
   else f(std::integral_constant<int, N>{}, std::integral_constant<int, 1>{});
 }
 template <typename F>
-void for_block_size(int n, int al, F&& f) {
-  switch (n) {
-    case 4: with_access_width<4>(al, f); break;
-    case 6: with_access_width<6>(al, f); break;
-    case 10: with_access_width<10>(al, f); break;
-    case 12: with_access_width<12>(al, f); break;
-    case 14: with_access_width<14>(al, f); break;
-    case 16: with_access_width<16>(al, f); break;
+void for_block_size(const BlockGeom& g, int al, F&& f) {
+  const bool even_rows = (g.nbw & 1) == 0;      // AL = 3: blocks pair up inside every row
+  switch (g.bs) {
+    case 4: with_access_width<4>(al, even_rows, f); break;
+    case 6: with_access_width<6>(al, even_rows, f); break;
+    case 10: with_access_width<10>(al, even_rows, f); break;
+    case 12: with_access_width<12>(al, even_rows, f); break;
+    case 14: with_access_width<14>(al, even_rows, f); break;
+    case 16: with_access_width<16>(al, even_rows, f); break;
     default: break;
   }
 }
@@ -200,7 +257,7 @@ void for_block_size(int n, int al, F&& f) {
 int launch_embed_fast_n(const uint8_t* rgb, uint8_t* out, const BlockGeom& g, const uint8_t* wm, int wm_shared,
                         double alpha, cudaStream_t st) {
   const unsigned grid = grid_for(g.total_blocks, kThreads);
-  for_block_size(g.bs, row_alignment(g, rgb, out), [&](auto n_, auto a_) {
+  for_block_size(g, row_alignment(g, rgb, out), [&](auto n_, auto a_) {
     k_embed_fast_n<decltype(n_)::value, decltype(a_)::value><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha);
   });
   return check_launch("embed kernel launch");
@@ -209,7 +266,7 @@ int launch_embed_fast_n(const uint8_t* rgb, uint8_t* out, const BlockGeom& g, co
 int launch_extract_fast_n(const uint8_t* wmk, const uint8_t* orig, uint8_t* out_wm, const BlockGeom& g, double alpha,
                           cudaStream_t st) {
   const unsigned grid = grid_for(g.total_blocks, kThreads);
-  for_block_size(g.bs, row_alignment(g, wmk, orig), [&](auto n_, auto a_) {
+  for_block_size(g, row_alignment(g, wmk, orig), [&](auto n_, auto a_) {
     k_extract_fast_n<decltype(n_)::value, decltype(a_)::value><<<grid, kThreads, 0, st>>>(wmk, orig, out_wm, g, alpha);
   });
   return check_launch("extract kernel launch");
@@ -217,7 +274,7 @@ int launch_extract_fast_n(const uint8_t* wmk, const uint8_t* orig, uint8_t* out_
 
 int launch_sigma0_fast_n(const uint8_t* rgb, float* sigma0, const BlockGeom& g, cudaStream_t st) {
   const unsigned grid = grid_for(g.total_blocks, kThreads);
-  for_block_size(g.bs, row_alignment(g, rgb, rgb), [&](auto n_, auto a_) {
+  for_block_size(g, row_alignment(g, rgb, rgb), [&](auto n_, auto a_) {
     k_sigma0_fast_n<decltype(n_)::value, decltype(a_)::value><<<grid, kThreads, 0, st>>>(rgb, sigma0, g);
   });
   return check_launch("sigma0 kernel launch");

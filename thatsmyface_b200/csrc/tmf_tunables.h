@@ -71,3 +71,18 @@
 #ifndef TMF_FAITHFUL_R1_MIN_CTAS
 #define TMF_FAITHFUL_R1_MIN_CTAS 3
 #endif
+
+// generic-N fast kernels (fast_n_kernels.cu): minimum CTAs of 128 threads per SM by block size
+// (4, 6 | 10 | 12 | 14, 16); the Gram matrix alone is N (N + 1) / 2 registers
+#ifndef TMF_FASTN_CTAS_SMALL
+#define TMF_FASTN_CTAS_SMALL 6
+#endif
+#ifndef TMF_FASTN_CTAS_10
+#define TMF_FASTN_CTAS_10 4
+#endif
+#ifndef TMF_FASTN_CTAS_12
+#define TMF_FASTN_CTAS_12 3
+#endif
+#ifndef TMF_FASTN_CTAS_LARGE
+#define TMF_FASTN_CTAS_LARGE 3
+#endif

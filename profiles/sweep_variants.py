@@ -26,11 +26,14 @@ def xtile(w, c, s, **kw):
     return d
 
 
-VARIANTS = {          # round 2, seventh sweep: occupancy of the generic-N fast kernels (run profiles/block_size_sweep.py per variant)
+VARIANTS = {          # round 2, eighth sweep: extract kernel shape after the full unroll of pass 1
     "base": {},
-    "n_large2": {"TMF_FASTN_CTAS_LARGE": 2},
-    "n_12c2_10c3": {"TMF_FASTN_CTAS_12": 2, "TMF_FASTN_CTAS_10": 3},
-    "n_12c4_10c5": {"TMF_FASTN_CTAS_12": 4, "TMF_FASTN_CTAS_10": 5, "TMF_FASTN_CTAS_LARGE": 4},
+    "x_c5": {"TMF_FAST_MIN_CTAS": 5},
+    "x_c7": {"TMF_FAST_MIN_CTAS": 7},
+    "x_c8": {"TMF_FAST_MIN_CTAS": 8},
+    "x_t64": {"TMF_EXTRACT_THREADS": 64},
+    "x_t128": {"TMF_EXTRACT_THREADS": 128},
+    "e_20x1_st1half": tile(20, 1, 1, 1),   # does not fit (stash): expected launch failure, kept as a guard
 }
 
 

@@ -26,14 +26,11 @@ def xtile(w, c, s, **kw):
     return d
 
 
-VARIANTS = {          # round 2, eighth sweep: extract kernel shape after the full unroll of pass 1
+VARIANTS = {          # round 2, ninth sweep: tile walk + TMA issue on the uniform datapath (k_embed_tile_u)
     "base": {},
-    "x_c5": {"TMF_FAST_MIN_CTAS": 5},
-    "x_c7": {"TMF_FAST_MIN_CTAS": 7},
-    "x_c8": {"TMF_FAST_MIN_CTAS": 8},
-    "x_t64": {"TMF_EXTRACT_THREADS": 64},
-    "x_t128": {"TMF_EXTRACT_THREADS": 128},
-    "e_20x1_st1half": tile(20, 1, 1, 1),   # does not fit (stash): expected launch failure, kept as a guard
+    "e_uniform": {"TMF_TILE_UNIFORM": 1},
+    "e_uniform_p2u8": {"TMF_TILE_UNIFORM": 1, "TMF_ROW_UNROLL_P2": 8},
+    "e_uniform_p2u2": {"TMF_TILE_UNIFORM": 1, "TMF_ROW_UNROLL_P2": 2},
 }
 
 

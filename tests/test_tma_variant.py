@@ -1,7 +1,7 @@
-"""The TMA-tiled persistent kernels (k_embed_tile / k_extract_tile, the default for 16-byte aligned
-batches whose rows hold a multiple of 16 blocks) against the per-thread kernels on the same pixels:
-the outputs must be identical (tests/tools/ab_tma.py: aligned buffers take the tile kernels, the
-same data at an 8-byte offset cannot)."""
+"""The TMA-tiled persistent embed kernel (k_embed_tile, the default for 16-byte aligned batches whose
+rows hold a multiple of 16 blocks) against the per-thread kernel on the same pixels: the outputs
+must be identical (tests/tools/ab_tma.py: aligned buffers take the tile kernel, the same data at an
+8-byte offset cannot).  Extract has one kernel; the tool checks it is insensitive to the offset too."""
 import os
 import re
 import subprocess
@@ -26,4 +26,4 @@ def test_tma_kernel_equals_per_thread_kernel(shape):
     counts = [int(m) for m in re.findall(r"mismatching samples (\d+) of", r.stdout)]
     assert len(counts) == 3 and counts == [0, 0, 0], r.stdout
     m = re.search(r"extract paths \([01], 0\): mismatching levels (\d+) of", r.stdout)
-    assert m and int(m.group(1)) == 0, r.stdout          # (tile extract is a build option: path 0 or 1)
+    assert m and int(m.group(1)) == 0, r.stdout

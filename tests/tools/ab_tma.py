@@ -1,6 +1,6 @@
-"""A/B check of the two FAST block-8 code paths on the same pixels: 16-byte aligned buffers take
-the TMA-tiled persistent kernels (k_embed_tile / k_extract_tile), the same data at an 8-byte offset
-takes the per-thread kernels.  Outputs must be identical.
+"""A/B check of the two FAST block-8 embed code paths on the same pixels: 16-byte aligned buffers take
+the TMA-tiled persistent kernel (k_embed_tile), the same data at an 8-byte offset takes the per-thread
+kernel.  Outputs must be identical.
 Usage: python tests/tools/ab_tma.py [n] [h] [w]"""
 import os
 import sys
@@ -49,7 +49,7 @@ for rep in range(3):
         rows = d.any(dim=3).any(dim=2).sum(1).tolist()
         print("  rows touched per image:", rows)
 
-# extract: tile kernel (aligned) against the per-thread kernel (offset copies) on the embedded images
+# extract (one kernel): aligned buffers against the offset copies of the embedded images
 ea = W.extract_tensor(a, imgs, 0.1, 8, 1)
 path_a = lib.tmf_last_fast_path()
 eb = W.extract_tensor(off_out, off_in, 0.1, 8, 1)

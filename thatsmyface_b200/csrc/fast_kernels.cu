@@ -2,13 +2,15 @@
 // certified power iteration on the 8x8 Gram matrix of the block's luma; the block itself is
 // never held in registers.
 //
-//   k_embed_tile / k_extract_tile   persistent kernels fed by the TMA engine: a warp owns a tile
-//       of 32 blocks (two boxes of 16 blocks x 8 image rows); ONE cp.async.bulk.tensor per box
-//       brings it into shared memory, both row passes run out of shared memory, pass 2 writes in
-//       place and ONE cp.async.bulk.tensor per box stores it.  The default wherever the batch is
-//       16-byte aligned and an image row holds a multiple of 16 blocks (512^2, 720p, 1080p, 4K, 8K).
+//   k_embed_tile   persistent embed kernel fed by the TMA engine: a warp owns a tile of 32 blocks
+//       (two boxes of 16 blocks x 8 image rows); ONE cp.async.bulk.tensor per box brings it into
+//       shared memory, both row passes run out of shared memory, pass 2 writes in place and ONE
+//       cp.async.bulk.tensor per box stores it.  The default wherever the batch is 16-byte aligned
+//       and an image row holds a multiple of 16 blocks (512^2, 720p, 1080p, 4K, 8K).
 //   k_embed_fast / k_extract_fast / k_sigma0_fast   one thread per block with per-thread global
-//       accesses: any size, any alignment.
+//       accesses: any size, any alignment.  Extract reads every byte once, so staging it through
+//       shared memory only costs occupancy: the per-thread kernel is its fastest form
+//       (a TMA-tiled extract measured 0.81-0.89 M MP/s against 1.02 M, profiles/r02_sweep_a_tile_shapes.txt).
 #include <cuda.h>   // CUtensorMap, cuTensorMapEncodeTiled's prototype (the entry point comes from the runtime)
 
 #include <atomic>
@@ -150,7 +152,7 @@ k_sigma0_fast(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, Block
 }
 
 // ---------------------------------------------------------------------------
-// TMA-tiled persistent kernels.
+// TMA-tiled persistent embed kernel.
 //
 // Why: with per-thread row accesses a warp's 64-bit load covers 256 useful bytes spread over
 // 768, i.e. 6-7 L1 wavefronts instead of 2, three times per row; the resident CTAs' rows do not
@@ -158,24 +160,29 @@ k_sigma0_fast(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, Block
 // 33 M load sectors for 6.2 M of input, L1 hit 58 %, 18 % of the warp samples on long_scoreboard),
 // and every 32-byte output sector reaches L2 in three partial writes.  Round 1's answer, eight
 // per-row cp.async.bulk per warp each way, fixed the memory side and lost on copy-issue
-// instructions (UBLKCP lives on the uniform datapath: a loop per lane).  Here:
+// instructions.  Here:
 //
 //   * the batch is ONE 3-D tensor (3W/4 words, H rows, N images; strides 3W and img_stride
 //     bytes), and a BOX is 16 blocks x 8 rows = 96 words x 8 rows = 3 KB;
 //   * a warp's TILE is two boxes, consecutive in the linear box order (same block-row, or
 //     wrapping to the next block-row / image): lane L owns block (L & 15) of box (L >> 4), so
 //     no lane idles whenever an image row holds a multiple of 16 blocks;
-//   * lanes 0 and 16 issue ONE cp.async.bulk.tensor.3d each (SASS UTMALDG) onto the warp's
-//     mbarrier; the warp waits, runs pass 1, the eigen-solve and pass 2 out of shared memory
-//     (three conflict-free LDS.64 / STS.64 per row: thread stride 24 B), writing its output
-//     bytes IN PLACE, and the same two lanes issue ONE cp.async.bulk.tensor.3d store each
-//     (UTMASTG): full-line writes, no per-thread STG, no address arithmetic per row;
-//   * the kernel is persistent: a warp walks tiles t, t + W, t + 2W, ... (W = warps in the
-//     grid).  With TMF_TILE_STAGES = 2 a warp has two tile buffers and asks for its NEXT tile
-//     before pass 2 of the current one, so the ~1 us a freshly launched warp used to wait for
-//     its first row is hidden behind its own arithmetic; with 1 it loads, computes, stores in
-//     turn and relies on the other resident warps.
-//   * warps never synchronise with each other: no __syncthreads after the barrier set-up.
+//   * one elected lane issues ONE cp.async.bulk.tensor.3d per box (SASS UTMALDG.3D) onto the
+//     warp's mbarrier; the warp waits, runs pass 1, the eigen-solve and pass 2 out of shared
+//     memory (three conflict-free LDS.64 / STS.64 per row: thread stride 24 B, constant offsets),
+//     writing its output bytes IN PLACE, and ONE cp.async.bulk.tensor.3d store per box
+//     (UTMASTG.3D) hands them back: full-line writes, no per-thread STG;
+//   * the kernel is persistent: a warp walks tiles t, t + W, t + 2W, ... (W = warps in the grid);
+//     warps never synchronise with each other.  Warps per CTA must be a multiple of 4: the walk
+//     is static, so a scheduler with one warp more than its neighbours sets the pace;
+//   * one 6 KB buffer per warp + the 8 KB luma stash = 16 warps per SM.  A single buffer cannot be
+//     refilled before it has been stored; what hides that turn-around is an L2 prefetch
+//     (cp.async.bulk.prefetch.tensor, UTMAPF.L2.3D) of the warp's NEXT tile, issued at the start of
+//     the current one: the load that follows the store finds its data in L2 (mbarrier wait 16 % ->
+//     2.6 % of the warp samples, 794 k -> 842 k MP/s).  Measured and dropped (tables in
+//     profiles/r02_sweep_*.txt): a second buffer without the stash (pass 2 recomputes the luma,
+//     +9 % instructions: no gain), the buffer handed over in halves (twice the copies and
+//     barriers: -7 %), 20-28 warps without stash (dispatch-bound: flat).
 // ---------------------------------------------------------------------------
 constexpr int kBoxBlocks = 16;                        // blocks per box row
 constexpr int kBoxRowBytes = kBoxBlocks * 24;         // 384
@@ -221,383 +228,141 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// where a lane's box sits: tensor coordinates of its first element and the map index of the lane's block
-struct BoxAt {
-  uint32_t c0, c1, c2;     // word column, image row, image
-  uint32_t map_idx;        // index of the lane's block in a per-image map (add image * blocks_per_img for per-image maps)
-  bool valid;
+// Tile control lives on the UNIFORM datapath: everything that is the same for the whole warp - the
+// tile index, both boxes' coordinates, the barrier phase - is computed once per tile, warp-uniformly
+// (the warp index comes from a shuffle, which tells the compiler so), and ONE elected lane issues
+// the loads / stores / prefetches of both boxes.  (A first version let lanes 0 and 16 compute their
+// own box and issue their own copies: the compiler serialised the two lanes and moved every operand
+// with R2UR, 157 of 1 904 instructions per tile; this form is +1.8 %, profiles/r02_sweep_i_uniform.txt.)
+// Lane-specific: only the map index of the lane's block.
+template <int WARPS>
+struct EmbedTileSmem {
+  static constexpr int kTiles = WARPS * kTileBytes;
+  static constexpr int kStash = WARPS * 32 * 32 * 8;                     // 32 float2 per thread
+  static constexpr int kBars = WARPS * 8;
+  static constexpr int kTotal = kTiles + kStash + kBars;
 };
-__device__ __forceinline__ BoxAt box_at(const TileGeom& tg, uint32_t box, uint32_t l16) {
-  BoxAt b;
-  b.valid = box < tg.total_boxes;
-  const uint32_t img = fastdiv(box, tg.div_bpi);
-  const uint32_t r = box - img * tg.boxes_per_img;
+
+struct TileAt {          // warp-uniform: tensor coordinates of the tile's two boxes
+  uint32_t c0a, c1a, c2a, c0b, c1b, c2b;
+  uint32_t nb;           // 2, or 1 for the last tile of an odd box count
+};
+__device__ __forceinline__ TileAt tile_at(const TileGeom& tg, uint32_t t) {
+  TileAt a;
+  const uint32_t b0 = 2u * t;
+  const uint32_t img = fastdiv(b0, tg.div_bpi);
+  const uint32_t r = b0 - img * tg.boxes_per_img;
   const uint32_t by = fastdiv(r, tg.div_bpr);
   const uint32_t bxb = r - by * tg.boxes_per_row;
-  b.c0 = bxb * (uint32_t)kBoxWords;
-  b.c1 = by * 8u;
-  b.c2 = img;
-  b.map_idx = by * tg.nbw + bxb * (uint32_t)kBoxBlocks + l16;
-  return b;
+  a.c0a = bxb * (uint32_t)kBoxWords; a.c1a = by * 8u; a.c2a = img;
+  a.nb = (b0 + 1u < tg.total_boxes) ? 2u : 1u;
+  const bool same_row = bxb + 1u < tg.boxes_per_row;
+  const bool same_img = r + 1u < tg.boxes_per_img;
+  a.c0b = same_row ? a.c0a + (uint32_t)kBoxWords : 0u;
+  a.c1b = same_row ? a.c1a : (same_img ? a.c1a + 8u : 0u);
+  a.c2b = same_img ? img : img + 1u;
+  return a;
 }
-
-template <int WARPS, int STAGES, bool STASH>
-struct EmbedTileSmem {
-  static constexpr int kTiles = WARPS * STAGES * kTileBytes;
-  static constexpr int kStash = STASH ? WARPS * 32 * 32 * 8 : 0;         // 32 float2 per thread
-  static constexpr int kBars = WARPS * STAGES * 8;
-  static constexpr int kTotal = kTiles + kStash + kBars;
-};
-
-template <int WARPS, int CTAS_PER_SM, int STAGES, bool STASH>
-__global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM)
-k_embed_tile(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap dst_map, TileGeom tg,
-             const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
-  using L = EmbedTileSmem<WARPS, STAGES, STASH>;
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t half = (uint32_t)lane >> 4, l16 = (uint32_t)lane & 15u;
-  const bool leader = l16 == 0;
-  uint8_t* tiles = smem + warp * (STAGES * kTileBytes);
-  const uint32_t tiles_s = smem_u32(tiles);
-  const uint32_t bars = smem_u32(smem + L::kTiles + L::kStash) + warp * (STAGES * 8);
-  float2* col = STASH ? reinterpret_cast<float2*>(smem + L::kTiles) + threadIdx.x : nullptr;
-  constexpr int kStride = WARPS * 32;
-
-  const uint32_t nwarps = gridDim.x * WARPS;
-  uint32_t t = blockIdx.x * WARPS + warp;
-  if (t >= tg.total_tiles) return;                    // whole warp; nothing below is CTA-wide
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(bars + 8 * s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-
-  const uint32_t lane_off = half * kBoxBytes + l16 * 24u;     // this lane's block inside a tile buffer
-  // ask for the first tile
-  BoxAt at = box_at(tg, 2u * t + half, l16);
-  {
-    const uint32_t nb = (2u * t + 1u < tg.total_boxes) ? 2u : 1u;
-    if (lane == 0) mbar_expect_tx(bars, nb * kBoxBytes);
-    __syncwarp();
-    if (leader && at.valid) tma_load_box(tiles_s + half * kBoxBytes, &src_map, at.c0, at.c1, at.c2, bars);
-  }
-  uint32_t mark = 0;
-  if (at.valid) mark = (uint32_t)__ldg(wm + (wm_shared ? 0u : at.c2 * tg.blocks_per_img) + at.map_idx);
-
-  for (uint32_t it = 0;; ++it) {
-    const uint32_t s = (STAGES == 2) ? (it & 1u) : 0u;
-    const uint32_t par = (STAGES == 2) ? ((it >> 1) & 1u) : (it & 1u);
-    uint8_t* mine = tiles + s * kTileBytes + lane_off;
-    const uint32_t tn = t + nwarps;
-    const bool more = tn < tg.total_tiles;
-    BoxAt nx = at;
-    uint32_t mark_n = 0;
-    if (STAGES == 1 && TMF_TILE_L2PF && more) {
-      // single buffer: the next tile cannot be loaded before this one is stored; ask L2 for it now,
-      // so that the load at the end of this iteration finds it there
-      nx = box_at(tg, 2u * tn + half, l16);
-      if (leader && nx.valid) tma_prefetch_box(&src_map, nx.c0, nx.c1, nx.c2);
-    }
-    mbar_wait(bars + 8 * s, par);
-
-    float w[8], f = 0.0f, c = 0.0f;
-    if (at.valid && mark != 0) {
-      float gm[36];
-      gram_of_block<0, STASH ? 2 : 0, kStride, uint32_t>(mine, (uint32_t)kBoxRowBytes, gm, col);
-      tmf::embed_block_scalars_fast(gm, alpha, mark, w, f, c, nullptr, TMF_LUMA_UNIT);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = 0.0f;
-    }
-
-    if (STAGES == 2 && more) {
-      // the other buffer's last store (issued at the end of the previous iteration by these two
-      // lanes) has long been read out; then ask for the next tile: it lands during pass 2
-      nx = box_at(tg, 2u * tn + half, l16);
-      if (leader) bulk_wait_read0();
-      const uint32_t nb = (2u * tn + 1u < tg.total_boxes) ? 2u : 1u;
-      if (lane == 0) mbar_expect_tx(bars + 8 * (s ^ 1u), nb * kBoxBytes);
-      __syncwarp();
-      if (leader && nx.valid)
-        tma_load_box(tiles_s + (s ^ 1u) * kTileBytes + half * kBoxBytes, &src_map, nx.c0, nx.c1, nx.c2, bars + 8 * (s ^ 1u));
-      if (nx.valid) mark_n = (uint32_t)__ldg(wm + (wm_shared ? 0u : nx.c2 * tg.blocks_per_img) + nx.map_idx);
-    }
-
-    if (at.valid) {
-      const float2 w2[4] = {make_float2(w[0], w[1]), make_float2(w[2], w[3]), make_float2(w[4], w[5]), make_float2(w[6], w[7])};
-#pragma unroll kRowUnrollP2
-      for (int i = 0; i < 8; ++i) {
-        uint32_t o[6], wd[6];
-        load_row24<0>(mine + i * kBoxRowBytes, wd);
-        float2 y2[4];
-        if (STASH) {
-#pragma unroll
-          for (int p = 0; p < 4; ++p) y2[p] = col[(4 * i + p) * kStride];     // unmarked lanes: stale values, unused
-        } else {
-          row_luma2(wd, y2);          // the same exact integers pass 1 had: identical results
-        }
-        embed_row_fast2(wd, y2, w2, f, c, o, mark != 0);
-        store_row24<0>(mine + i * kBoxRowBytes, o);
-      }
-    }
-    // generic-proxy writes -> visible to the async proxy, then the two leaders hand their boxes over
-    fence_async_smem();
-    __syncwarp();
-    if (leader && at.valid) {
-      tma_store_box(&dst_map, at.c0, at.c1, at.c2, tiles_s + s * kTileBytes + half * kBoxBytes);
-      bulk_commit();
-    }
-    if (!more) break;
-    if (STAGES == 1) {
-      // single buffer: wait until the store has read it, then refill it
-      if (!TMF_TILE_L2PF) nx = box_at(tg, 2u * tn + half, l16);
-      if (leader) bulk_wait_read0();
-      const uint32_t nb = (2u * tn + 1u < tg.total_boxes) ? 2u : 1u;
-      if (lane == 0) mbar_expect_tx(bars, nb * kBoxBytes);
-      __syncwarp();
-      if (leader && nx.valid) tma_load_box(tiles_s + half * kBoxBytes, &src_map, nx.c0, nx.c1, nx.c2, bars);
-      if (nx.valid) mark_n = (uint32_t)__ldg(wm + (wm_shared ? 0u : nx.c2 * tg.blocks_per_img) + nx.map_idx);
-    }
-    t = tn;
-    at = nx;
-    mark = mark_n;
-  }
-  if (leader) bulk_wait_read0();     // shared memory must outlive the last store's reads
-}
-
-// ---------------------------------------------------------------------------
-// k_embed_tile_split: the single-buffer tile kernel with the buffer handed over in HALVES.
-//
-// A single buffer cannot be refilled before it has been stored, so in k_embed_tile<.., 1, ..> a warp
-// idles from "store issued" to "next tile landed" (ncu: 16 % of its samples sit in the mbarrier
-// wait), and a second buffer does not fit beside the luma stash (6 + 6 + 8 KB per warp = 11 warps
-// per SM).  Here the tile is moved as FOUR boxes of 16 blocks x 4 rows (upper / lower half of each
-// of the two boxes, a tensor map with a 4-row box), each half with its own mbarrier:
-//   pass 2 rows 0-3 done  -> store the upper halves
-//   pass 2 rows 4-5 done  -> the upper store has been read out long ago: load the NEXT tile's
-//                            upper halves (they land while rows 6-7 and the solve's tail run)
-//   pass 2 rows 6-7 done  -> store the lower halves, wait for that read, load the next lower halves
-//   next tile: pass 1 waits for the upper halves (there already), runs rows 0-3, then waits for the
-//   lower halves (in flight since the end of the previous tile; L2-prefetched at its start).
-// Same arithmetic and same results as the other FAST block-8 kernels.
-// ---------------------------------------------------------------------------
-constexpr int kHalfBoxBytes = 4 * kBoxRowBytes;       // 1536
-constexpr int kHalfTileBytes = 2 * kHalfBoxBytes;     // 3072: both boxes' upper (or lower) halves
-
-template <int WARPS>
-struct EmbedSplitSmem {
-  static constexpr int kTiles = WARPS * kTileBytes;
-  static constexpr int kStash = WARPS * 32 * 32 * 8;
-  static constexpr int kBars = WARPS * 2 * 8;
-  static constexpr int kTotal = kTiles + kStash + kBars;
-};
-
-// Gram update from 4 consecutive rows (i0 .. i0+3) of a staged half box
-template <int STRIDE>
-__device__ __forceinline__ void gram_rows4(const uint8_t* __restrict__ rows, int i0, GramPairs& G, float2* __restrict__ col) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint32_t w[6];
-    float2 y2[4];
-    load_row24<0>(rows + i * kBoxRowBytes, w);
-    row_luma2(w, y2);
-#pragma unroll
-    for (int p = 0; p < 4; ++p) col[(4 * (i0 + i) + p) * STRIDE] = y2[p];
-    gram_accumulate_row2(y2, G);
-  }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 template <int WARPS, int CTAS_PER_SM>
 __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM)
-k_embed_tile_split(const __grid_constant__ CUtensorMap src_map8, const __grid_constant__ CUtensorMap src_map4,
-                   const __grid_constant__ CUtensorMap dst_map4, TileGeom tg, const uint8_t* __restrict__ wm,
-                   int wm_shared, double alpha) {
-  using L = EmbedSplitSmem<WARPS>;
+k_embed_tile(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap dst_map, TileGeom tg,
+               const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
+  using L = EmbedTileSmem<WARPS>;
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t half = (uint32_t)lane >> 4, l16 = (uint32_t)lane & 15u;
-  const bool leader = l16 == 0;
+  const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);       // warp-uniform, and the compiler knows it
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t half = lane >> 4, l16 = lane & 15u;
   uint8_t* tiles = smem + warp * kTileBytes;
-  const uint32_t tiles_s = smem_u32(tiles);
-  const uint32_t bars = smem_u32(smem + L::kTiles + L::kStash) + warp * 16;     // [0] upper halves, [8] lower halves
+  const uint32_t tiles_s = smem_u32(smem) + warp * kTileBytes;
+  const uint32_t bar = smem_u32(smem) + L::kTiles + L::kStash + warp * 8;
   float2* col = reinterpret_cast<float2*>(smem + L::kTiles) + threadIdx.x;
   constexpr int kStride = WARPS * 32;
 
   const uint32_t nwarps = gridDim.x * WARPS;
   uint32_t t = blockIdx.x * WARPS + warp;
   if (t >= tg.total_tiles) return;                    // whole warp; nothing below is CTA-wide
-  if (lane == 0) {
-    mbar_init(bars, 1);
-    mbar_init(bars + 8, 1);
+  if (elect_one()) {
+    mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
 
-  // this lane's block: row r of half h at  mine + h * kHalfTileBytes + r * kBoxRowBytes
-  uint8_t* mine = tiles + half * kHalfBoxBytes + l16 * 24u;
-  const uint32_t box_s = tiles_s + half * kHalfBoxBytes;      // this leader's half box (upper; + kHalfTileBytes = lower)
-
-  auto load_half = [&](uint32_t tile, const BoxAt& b, uint32_t h) {
-    const uint32_t nb = (2u * tile + 1u < tg.total_boxes) ? 2u : 1u;
-    if (lane == 0) mbar_expect_tx(bars + 8 * h, nb * kHalfBoxBytes);
-    __syncwarp();
-    if (leader && b.valid) tma_load_box(box_s + h * kHalfTileBytes, &src_map4, b.c0, b.c1 + 4u * h, b.c2, bars + 8 * h);
+  auto load_tile = [&](const TileAt& a) {              // by ONE lane: both boxes onto the warp's barrier
+    mbar_expect_tx(bar, a.nb * kBoxBytes);
+    tma_load_box(tiles_s, &src_map, a.c0a, a.c1a, a.c2a, bar);
+    if (a.nb == 2u) tma_load_box(tiles_s + kBoxBytes, &src_map, a.c0b, a.c1b, a.c2b, bar);
+  };
+  auto lane_mark = [&](const TileAt& a) -> uint32_t {  // the lane's watermark value (0 for a missing second box)
+    const uint32_t c0 = half ? a.c0b : a.c0a, c1 = half ? a.c1b : a.c1a, c2 = half ? a.c2b : a.c2a;
+    if (half && a.nb != 2u) return 0u;
+    const uint32_t bx16 = (c0 * 43691u) >> 18;         // c0 / 6 for c0 < 2^16 ... (c0 = 96 * box column: exact)
+    const uint32_t idx = (c1 >> 3) * tg.nbw + bx16 + l16;
+    return (uint32_t)__ldg(wm + (wm_shared ? 0u : c2 * tg.blocks_per_img) + idx);
   };
 
-  BoxAt at = box_at(tg, 2u * t + half, l16);
-  load_half(t, at, 0);
-  load_half(t, at, 1);
-  uint32_t mark = 0;
-  if (at.valid) mark = (uint32_t)__ldg(wm + (wm_shared ? 0u : at.c2 * tg.blocks_per_img) + at.map_idx);
+  TileAt at = tile_at(tg, t);
+  if (elect_one()) load_tile(at);
+  uint32_t mark = lane_mark(at);
+  uint8_t* mine = tiles + half * kBoxBytes + l16 * 24u;
 
   for (uint32_t it = 0;; ++it) {
-    const uint32_t par = it & 1u;
     const uint32_t tn = t + nwarps;
     const bool more = tn < tg.total_tiles;
-    BoxAt nx = at;
+    const bool valid = !(half && at.nb != 2u);
+    TileAt nx = at;
     uint32_t mark_n = 0;
     if (more) {
-      nx = box_at(tg, 2u * tn + half, l16);
-      if (leader && nx.valid) tma_prefetch_box(&src_map8, nx.c0, nx.c1, nx.c2);      // the whole box, into L2
-      if (nx.valid) mark_n = (uint32_t)__ldg(wm + (wm_shared ? 0u : nx.c2 * tg.blocks_per_img) + nx.map_idx);
+      nx = tile_at(tg, tn);
+      if (elect_one()) {                               // ask L2 for the next tile now: the load after the store finds it there
+        tma_prefetch_box(&src_map, nx.c0a, nx.c1a, nx.c2a);
+        if (nx.nb == 2u) tma_prefetch_box(&src_map, nx.c0b, nx.c1b, nx.c2b);
+      }
+      mark_n = lane_mark(nx);
     }
-    const bool marked = at.valid && mark != 0;
+    mbar_wait(bar, it & 1u);
 
-    // pass 1, half by half
-    GramPairs G;
-    gram_clear(G);
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-      mbar_wait(bars + 8 * h, par);
-      if (marked) gram_rows4<kStride>(mine + h * kHalfTileBytes, 4 * h, G, col);
-    }
     float w[8], f = 0.0f, c = 0.0f;
-    if (marked) {
+    if (valid && mark != 0) {
       float gm[36];
-      gram_pairs_to_sym(G, gm);
+      gram_of_block<0, 2, kStride, uint32_t>(mine, (uint32_t)kBoxRowBytes, gm, col);
       tmf::embed_block_scalars_fast(gm, alpha, mark, w, f, c, nullptr, TMF_LUMA_UNIT);
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) w[i] = 0.0f;
     }
-
-    // pass 2, two rows at a time, the halves handed over as they complete
-    const float2 w2[4] = {make_float2(w[0], w[1]), make_float2(w[2], w[3]), make_float2(w[4], w[5]), make_float2(w[6], w[7])};
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-      if (at.valid) {
-        uint8_t* rows = mine + (q >> 1) * kHalfTileBytes + (q & 1) * (2 * kBoxRowBytes);
+    if (valid) {
+      const float2 w2[4] = {make_float2(w[0], w[1]), make_float2(w[2], w[3]), make_float2(w[4], w[5]), make_float2(w[6], w[7])};
+#pragma unroll kRowUnrollP2
+      for (int i = 0; i < 8; ++i) {
+        uint32_t o[6], wd[6];
+        load_row24<0>(mine + i * kBoxRowBytes, wd);
+        float2 y2[4];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          uint32_t o[6], wd[6];
-          float2 y2[4];
-          load_row24<0>(rows + r * kBoxRowBytes, wd);
-#pragma unroll
-          for (int p = 0; p < 4; ++p) y2[p] = col[(4 * (2 * q + r) + p) * kStride];     // unmarked lanes: stale values, unused
-          embed_row_fast2(wd, y2, w2, f, c, o, mark != 0);
-          store_row24<0>(rows + r * kBoxRowBytes, o);
-        }
-      }
-      if (q == 1 || q == 3) {
-        // generic-proxy writes -> visible to the async proxy, then the two leaders hand their half boxes over
-        const uint32_t h = (uint32_t)q >> 1;
-        fence_async_smem();
-        __syncwarp();
-        if (leader && at.valid) {
-          tma_store_box(&dst_map4, at.c0, at.c1 + 4u * h, at.c2, box_s + h * kHalfTileBytes);
-          bulk_commit();
-        }
-      } else if (q == 2 && more) {
-        if (leader) bulk_wait_read0();              // the upper halves' store (issued two rows ago) has been read out
-        load_half(tn, nx, 0);
+        for (int p = 0; p < 4; ++p) y2[p] = col[(4 * i + p) * kStride];       // unmarked lanes: stale values, unused
+        embed_row_fast2(wd, y2, w2, f, c, o, mark != 0);
+        store_row24<0>(mine + i * kBoxRowBytes, o);
       }
     }
+    // generic-proxy writes -> visible to the async proxy, then one lane hands both boxes over
+    fence_async_smem();
+    __syncwarp();
+    if (elect_one()) {
+      tma_store_box(&dst_map, at.c0a, at.c1a, at.c2a, tiles_s);
+      if (at.nb == 2u) tma_store_box(&dst_map, at.c0b, at.c1b, at.c2b, tiles_s + kBoxBytes);
+      bulk_commit();
+      bulk_wait_read0();                               // the buffer has been read out: refill it (or leave)
+      if (more) load_tile(nx);
+    }
     if (!more) break;
-    if (leader) bulk_wait_read0();
-    load_half(tn, nx, 1);
     t = tn;
     at = nx;
     mark = mark_n;
-  }
-  if (leader) bulk_wait_read0();     // shared memory must outlive the last store's reads
-}
-
-// Fused extract, TMA-tiled: the same tile walk over TWO tensors (watermarked, original); a
-// stage holds both tiles (12 KB per warp), pass 1 + eigen-solve run once per image out of
-// shared memory, and the lane writes its one output byte (32 contiguous bytes per warp).
-template <int WARPS, int STAGES>
-struct ExtractTileSmem {
-  static constexpr int kTiles = WARPS * STAGES * 2 * kTileBytes;
-  static constexpr int kBars = WARPS * STAGES * 8;
-  static constexpr int kTotal = kTiles + kBars;
-};
-
-template <int WARPS, int CTAS_PER_SM, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM)
-k_extract_tile(const __grid_constant__ CUtensorMap wmk_map, const __grid_constant__ CUtensorMap orig_map, TileGeom tg,
-               uint8_t* __restrict__ out_wm, double alpha) {
-  using L = ExtractTileSmem<WARPS, STAGES>;
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t half = (uint32_t)lane >> 4, l16 = (uint32_t)lane & 15u;
-  const bool leader = l16 == 0;
-  uint8_t* tiles = smem + warp * (STAGES * 2 * kTileBytes);
-  const uint32_t tiles_s = smem_u32(tiles);
-  const uint32_t bars = smem_u32(smem + L::kTiles) + warp * (STAGES * 8);
-
-  const uint32_t nwarps = gridDim.x * WARPS;
-  uint32_t t = blockIdx.x * WARPS + warp;
-  if (t >= tg.total_tiles) return;
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(bars + 8 * s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  const uint32_t lane_off = half * kBoxBytes + l16 * 24u;
-
-  auto request = [&](uint32_t tile, uint32_t stage, const BoxAt& b) {
-    const uint32_t nb = (2u * tile + 1u < tg.total_boxes) ? 2u : 1u;
-    if (lane == 0) mbar_expect_tx(bars + 8 * stage, 2u * nb * kBoxBytes);
-    __syncwarp();
-    if (leader && b.valid) {
-      const uint32_t dst = tiles_s + stage * (2 * kTileBytes) + half * kBoxBytes;
-      tma_load_box(dst, &wmk_map, b.c0, b.c1, b.c2, bars + 8 * stage);
-      tma_load_box(dst + kTileBytes, &orig_map, b.c0, b.c1, b.c2, bars + 8 * stage);
-    }
-  };
-
-  BoxAt at = box_at(tg, 2u * t + half, l16);
-  request(t, 0, at);
-  if (STAGES == 2 && t + nwarps < tg.total_tiles) request(t + nwarps, 1, box_at(tg, 2u * (t + nwarps) + half, l16));
-
-  for (uint32_t it = 0;; ++it) {
-    const uint32_t s = (STAGES == 2) ? (it & 1u) : 0u;
-    const uint32_t par = (STAGES == 2) ? ((it >> 1) & 1u) : (it & 1u);
-    const uint8_t* mine = tiles + s * (2 * kTileBytes) + lane_off;
-    mbar_wait(bars + 8 * s, par);
-    float sw = 0.0f, so = 0.0f;
-    if (at.valid) {
-#pragma unroll 1
-      for (int which = 0; which < 2; ++which) {
-        float gm[36];
-        gram_of_block<0, 0, 1, uint32_t>(mine + which * kTileBytes, (uint32_t)kBoxRowBytes, gm);
-        const float sg = tmf::sigma0_from_gram_fast(gm, nullptr, TMF_LUMA_UNIT);
-        if (which == 0) sw = sg; else so = sg;
-      }
-      out_wm[at.c2 * tg.blocks_per_img + at.map_idx] = (uint8_t)tmf::extract_level(sw, so, alpha);
-    }
-    // this stage is free again (only generic-proxy reads touched it): refill it with the tile
-    // STAGES steps ahead
-    const uint32_t tn = t + nwarps;
-    if (tn >= tg.total_tiles) break;
-    const uint32_t tr = t + STAGES * nwarps;
-    __syncwarp();                                    // every lane has finished reading the stage
-    if (tr < tg.total_tiles) request(tr, s, box_at(tg, 2u * tr + half, l16));
-    t = tn;
-    at = box_at(tg, 2u * t + half, l16);
   }
 }
 
@@ -646,12 +411,12 @@ int make_tile_geom(const BlockGeom& g, TileGeom& tg) {
   return TMF_OK;
 }
 
-int make_map(CUtensorMap* m, const void* base, const BlockGeom& g, int n, unsigned box_rows = 8) {
+int make_map(CUtensorMap* m, const void* base, const BlockGeom& g, int n) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(TMF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[3] = {(cuuint64_t)(g.row_pitch / 4), (cuuint64_t)g.nbh * 8u, (cuuint64_t)n};
   const cuuint64_t strides[2] = {(cuuint64_t)g.row_pitch, (cuuint64_t)g.img_stride};
-  const cuuint32_t box[3] = {(cuuint32_t)kBoxWords, box_rows, 1u};
+  const cuuint32_t box[3] = {(cuuint32_t)kBoxWords, 8u, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -678,30 +443,10 @@ int last_fast_path() { return g_last_path; }
 
 int launch_embed_fast8(const uint8_t* rgb, uint8_t* out, const BlockGeom& g, const uint8_t* wm, int wm_shared,
                        double alpha, cudaStream_t st) {
-  if (TMF_TILE_SPLIT && tile_ok(g, rgb, out)) {
-    constexpr int W = TMF_TILE_WARPS, C = TMF_TILE_CTAS_PER_SM;
-    auto kernel = k_embed_tile_split<W, C>;
-    constexpr int smem = EmbedSplitSmem<W>::kTotal;
-    static std::atomic<unsigned long long> done{0};
-    if (int rc = set_smem(kernel, smem, done)) return rc;
-    TileGeom tg;
-    make_tile_geom(g, tg);
-    const int n = (int)(g.total_blocks / g.blocks_per_img);
-    CUtensorMap m8, ms, md;
-    if (int rc = make_map(&m8, rgb, g, n, 8)) return rc;
-    if (int rc = make_map(&ms, rgb, g, n, 4)) return rc;
-    if (int rc = make_map(&md, out, g, n, 4)) return rc;
-    const unsigned cap = (unsigned)sm_count() * C;
-    const unsigned need = grid_for(tg.total_tiles, W);
-    kernel<<<need < cap ? need : cap, W * 32, smem, st>>>(m8, ms, md, tg, wm, wm_shared, alpha);
-    g_last_path = 1;
-    return check_launch("embed (tile) kernel launch");
-  }
   if (tile_ok(g, rgb, out)) {
-    constexpr int W = TMF_TILE_WARPS, C = TMF_TILE_CTAS_PER_SM, S = TMF_TILE_STAGES;
-    constexpr bool STASH = TMF_TILE_STASH != 0;
-    auto kernel = k_embed_tile<W, C, S, STASH>;
-    constexpr int smem = EmbedTileSmem<W, S, STASH>::kTotal;
+    constexpr int W = TMF_TILE_WARPS, C = TMF_TILE_CTAS_PER_SM;
+    auto kernel = k_embed_tile<W, C>;
+    constexpr int smem = EmbedTileSmem<W>::kTotal;
     static std::atomic<unsigned long long> done{0};
     if (int rc = set_smem(kernel, smem, done)) return rc;
     TileGeom tg;
@@ -728,24 +473,6 @@ int launch_embed_fast8(const uint8_t* rgb, uint8_t* out, const BlockGeom& g, con
 
 int launch_extract_fast8(const uint8_t* wmk, const uint8_t* orig, uint8_t* out_wm, const BlockGeom& g, double alpha,
                          cudaStream_t st) {
-  if (TMF_XTILE_ENABLE && tile_ok(g, wmk, orig)) {
-    constexpr int W = TMF_XTILE_WARPS, C = TMF_XTILE_CTAS_PER_SM, S = TMF_XTILE_STAGES;
-    auto kernel = k_extract_tile<W, C, S>;
-    constexpr int smem = ExtractTileSmem<W, S>::kTotal;
-    static std::atomic<unsigned long long> done{0};
-    if (int rc = set_smem(kernel, smem, done)) return rc;
-    TileGeom tg;
-    make_tile_geom(g, tg);
-    const int n = (int)(g.total_blocks / g.blocks_per_img);
-    CUtensorMap mw, mo;
-    if (int rc = make_map(&mw, wmk, g, n)) return rc;
-    if (int rc = make_map(&mo, orig, g, n)) return rc;
-    const unsigned cap = (unsigned)sm_count() * C;
-    const unsigned need = grid_for(tg.total_tiles, W);
-    kernel<<<need < cap ? need : cap, W * 32, smem, st>>>(mw, mo, tg, out_wm, alpha);
-    g_last_path = 1;
-    return check_launch("extract (tile) kernel launch");
-  }
   const unsigned grid = grid_for(g.total_blocks, kExtractThreads);
   switch (pick_vec(g, wmk, orig)) {
     case 8: k_extract_fast<8><<<grid, kExtractThreads, 0, st>>>(wmk, orig, out_wm, g, alpha); break;

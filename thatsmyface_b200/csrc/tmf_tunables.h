@@ -1,7 +1,7 @@
 // Launch-shape knobs of the fused kernels - the ONLY compile-time tunables of the library.
 // profiles/sweep_variants.py rebuilds the library with -D overrides of these and times the
 // alternatives on the GPU; the defaults below are the measured winners
-// (profiles/r01_sweep_variants.txt, profiles/r02_sweep_variants.txt).  Every knob whose sweep
+// (profiles/r01_sweep_variants.txt, profiles/r02_sweep_*.txt).  Every knob whose sweep
 // verdict was "loses" has been deleted together with its code path; the tables are the record.
 #pragma once
 
@@ -28,39 +28,13 @@
 #define TMF_FAST_MIN_CTAS 6      // extract / sigma0: 80 registers
 #endif
 
-// TMA-tiled persistent embed kernel (k_embed_tile): warps per CTA, CTAs per SM, smem stages per
-// warp (1 = load / compute / store in turn, 2 = the next tile's load in flight during pass 2),
-// and whether pass 1 parks the luma in shared memory (1) or pass 2 recomputes it (0)
+// TMA-tiled persistent embed kernel (k_embed_tile): warps per CTA (a multiple of 4) and CTAs per SM;
+// a warp needs 14 KB of shared memory (tile + luma stash), so 16 warps fill an SM
 #ifndef TMF_TILE_WARPS
 #define TMF_TILE_WARPS 16
 #endif
 #ifndef TMF_TILE_CTAS_PER_SM
 #define TMF_TILE_CTAS_PER_SM 1
-#endif
-#ifndef TMF_TILE_STAGES
-#define TMF_TILE_STAGES 1
-#endif
-#ifndef TMF_TILE_STASH
-#define TMF_TILE_STASH 1
-#endif
-#ifndef TMF_TILE_SPLIT
-#define TMF_TILE_SPLIT 0         // 1: k_embed_tile_split (single buffer + stash, handed over in halves)
-#endif
-#ifndef TMF_TILE_L2PF
-#define TMF_TILE_L2PF 1          // single-stage tiles: L2 prefetch of the warp's next tile at the start of this one
-#endif
-// the same for the TMA-tiled extract kernel (k_extract_tile; it has no stash)
-#ifndef TMF_XTILE_WARPS
-#define TMF_XTILE_WARPS 4
-#endif
-#ifndef TMF_XTILE_CTAS_PER_SM
-#define TMF_XTILE_CTAS_PER_SM 4
-#endif
-#ifndef TMF_XTILE_STAGES
-#define TMF_XTILE_STAGES 1
-#endif
-#ifndef TMF_XTILE_ENABLE
-#define TMF_XTILE_ENABLE 0       // 0: extract always takes the per-thread kernel
 #endif
 
 // faithful kernels, block size 8: minimum CTAs of 128 threads per SM - the literal form (A and V

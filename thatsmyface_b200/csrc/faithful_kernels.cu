@@ -25,6 +25,14 @@
 namespace tmfi {
 namespace {
 
+// f32(byte) / 255.0 of byte B of a row held in words: the byte is extracted straight onto the 2^23
+// magic number (one PRMT; a shift + mask + or would be two logic operations)
+template <int NW>
+__device__ __forceinline__ float unit_of_byte(const uint32_t (&w)[NW], int B) {
+  const float km = __uint_as_float(__byte_perm(w[B >> 2], 0x4B000000u, 0x7650u | (uint32_t)(B & 3)));
+  return tmf::unit_from_float_byte(km - 8388608.0f);
+}
+
 // ---------------------------------------------------------------------------
 // block size 8
 // ---------------------------------------------------------------------------
@@ -41,9 +49,9 @@ __device__ __forceinline__ void luma_rows_to_smem(const uint8_t* __restrict__ ba
     load_row24<VEC>(base + (size_t)i * pitch, w);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float r = tmf::unit_from_u8(TMF_BYTE(w, 3 * j));
-      const float g = tmf::unit_from_u8(TMF_BYTE(w, 3 * j + 1));
-      const float b = tmf::unit_from_u8(TMF_BYTE(w, 3 * j + 2));
+      const float r = unit_of_byte(w, 3 * j);
+      const float g = unit_of_byte(w, 3 * j + 1);
+      const float b = unit_of_byte(w, 3 * j + 2);
       col[(8 * i + j) * kThreads] = tmf::luma_exact(r, g, b);
     }
   }
@@ -67,9 +75,9 @@ __device__ __forceinline__ void colour_rows_out(const uint8_t* __restrict__ src,
     load_row24<VEC>(src + (size_t)i * pitch, w);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float r = tmf::unit_from_u8(TMF_BYTE(w, 3 * j));
-      const float gg = tmf::unit_from_u8(TMF_BYTE(w, 3 * j + 1));
-      const float b = tmf::unit_from_u8(TMF_BYTE(w, 3 * j + 2));
+      const float r = unit_of_byte(w, 3 * j);
+      const float gg = unit_of_byte(w, 3 * j + 1);
+      const float b = unit_of_byte(w, 3 * j + 2);
       float cb, cr;
       tmf::chroma_exact(r, gg, b, cb, cr);
       uint32_t R, G, B;
@@ -286,9 +294,9 @@ __device__ __forceinline__ void luma_block_to_smem(const uint8_t* __restrict__ b
     load_row_n<N, AL>(base + (size_t)i * pitch, w);
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      const float r = tmf::unit_from_u8(TMF_BYTE(w, 3 * j));
-      const float g = tmf::unit_from_u8(TMF_BYTE(w, 3 * j + 1));
-      const float b = tmf::unit_from_u8(TMF_BYTE(w, 3 * j + 2));
+      const float r = unit_of_byte(w, 3 * j);
+      const float g = unit_of_byte(w, 3 * j + 1);
+      const float b = unit_of_byte(w, 3 * j + 2);
       m[(i * N + j) * T] = tmf::luma_exact(r, g, b);
     }
   }
@@ -386,9 +394,9 @@ k_embed_faithful_n(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, B
     for (int k = 0; k < kRowWords<N>; ++k) o[k] = 0;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      const float r = tmf::unit_from_u8(TMF_BYTE(w, 3 * j));
-      const float gg = tmf::unit_from_u8(TMF_BYTE(w, 3 * j + 1));
-      const float b = tmf::unit_from_u8(TMF_BYTE(w, 3 * j + 2));
+      const float r = unit_of_byte(w, 3 * j);
+      const float gg = unit_of_byte(w, 3 * j + 1);
+      const float b = unit_of_byte(w, 3 * j + 2);
       float cb, cr;
       tmf::chroma_exact(r, gg, b, cb, cr);
       uint32_t R, G, B;

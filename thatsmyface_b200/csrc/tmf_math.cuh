@@ -89,6 +89,13 @@ TMF_HD float f_rsqrt(float x) {   // 1/sqrt(x), a few ulp; refined by the caller
   return 1.0f / sqrtf(x);
 #endif
 }
+TMF_HD float f_rsqrt_fast(float x) {   // for x >= 2^-126 (no subnormal fix-up code around the MUFU)
+#if defined(__CUDA_ARCH__)
+  float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
 TMF_HD float f_sqrt_fast(float x) {
 #if defined(__CUDA_ARCH__)
   float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
@@ -119,6 +126,16 @@ TMF_HD float dot3_npdot(double t0, double t1, double t2, float x0, float x1, flo
   return (float)acc;
 }
 
+// f32(u8) / 255.0 (below) from the byte already converted to float (callers that extract it from a packed word
+// straight onto the 2^23 magic number)
+TMF_HD float unit_from_float_byte(float k) {
+  const float r = 0.00392156885936856270f;        // RN32(1/255)
+  const float q0 = f_mul(k, r);
+  const float e = fmaf(-q0, 255.0f, k);           // exact residual
+  return fmaf(e, r, q0);
+}
+
+
 // watermarking.py:29 - f32(u8) / 255.0 (IEEE float32 division).  For the 256
 // possible inputs the quotient is reproduced exactly by one FMA-corrected
 // reciprocal step (checked for every byte by tests/test_hostsim.py and by the
@@ -131,12 +148,8 @@ TMF_HD float unit_from_u8(uint32_t v) {
 #else
   const float k = (float)v;
 #endif
-  const float r = 0.00392156885936856270f;        // RN32(1/255)
-  const float q0 = f_mul(k, r);
-  const float e = fmaf(-q0, 255.0f, k);           // exact residual
-  return fmaf(e, r, q0);
+  return unit_from_float_byte(k);
 }
-
 // watermarking.py:37-48 (Y only)
 TMF_HD float luma_exact(float r, float g, float b) {
   return dot3_npdot(0.299, 0.587, 0.114, r, g, b);
@@ -256,7 +269,7 @@ TMF_HD void idct8x8(float* a) {
 #define TMF_JACOBI_F32X2 1             // packed-fp32 rounds on the device (0: scalar rounds)
 #endif
 #define TMF_JACOBI_TOL 1.0e-6f
-#define TMF_JACOBI_DONE 3.0e-4f        // see the stop rule below
+#define TMF_JACOBI_DONE 1.0e-3f        // see the stop rule below
 #define TMF_JACOBI_MORE 1.5f          // jacobi_cs returned 2 for some pair of the sweep
 #define TMF_JACOBI_FLOOR 1.0e-14f      // (eps * ||A||_F)^2 with ||A||_F ~ 1
 #define TMF_JACOBI_MAX_SWEEPS 12
@@ -288,7 +301,7 @@ TMF_HD float pow2_scale_for(float frob2, float& unscale) {
 // left alone ((c, s) = (1, 0)), 1 if it is rotated, 2 if it is rotated and its |cosine| was
 // above TMF_JACOBI_DONE (another sweep is needed).  The cosine tests are done on squares,
 // ga^2 against tol^2 al be: no division, no square root.  Branch-free.
-TMF_HD float jacobi_cs(float al, float be, float ga, float& c, float& s) {
+TMF_HD float jacobi_cs(float al, float be, float ga, float& c, float& s, float* tan_out = nullptr) {
   const float ab = al * be;
   const float gg = ga * ga;
   const float g2 = ga + ga;
@@ -298,10 +311,11 @@ TMF_HD float jacobi_cs(float al, float be, float ga, float& c, float& s) {
   const float r = f_sqrt_fast(fmaf(g2, g2, d * d));
   const float t = g2 * f_rcp_fast(d + copysignf(r, d));
   const float tt = fmaf(t, t, 1.0f);
-  float cc = f_rsqrt(tt);
+  float cc = f_rsqrt_fast(tt);                         // tt >= 1
   cc = fmaf(0.5f * cc, fmaf(-tt * cc, cc, 1.0f), cc);  // one Newton step: c^2 + s^2 = 1 to ~1 ulp
   c = rot ? cc : 1.0f;
   s = rot ? cc * t : 0.0f;
+  if (tan_out) *tan_out = rot ? t : 0.0f;
   return rot ? ((gg > (TMF_JACOBI_DONE * TMF_JACOBI_DONE) * ab) ? 2.0f : 1.0f) : 0.0f;
 }
 
@@ -411,9 +425,10 @@ __device__ __forceinline__ float jacobi_round2(float2* a2, float2* v2, float* n2
     }
     const float g = ga.x + ga.y;
     const float al = WITH_V ? al2.x + al2.y : n2[2 * k], be = WITH_V ? be2.x + be2.y : n2[2 * k + 1];
-    worst = fmaxf(worst, jacobi_cs(al, be, g, c[k], s[k]));
+    float t;
+    worst = fmaxf(worst, jacobi_cs(al, be, g, c[k], s[k], &t));
     if (!WITH_V) {
-      const float tg = (s[k] * f_rcp_fast(c[k])) * g;        // t * gamma (0 when the pair is skipped: s = 0)
+      const float tg = t * g;                                // t * gamma (0 when the pair is skipped)
       nn[TMF_PI(2 * k)] = fmaxf(al - tg, 0.0f);
       nn[TMF_PI(2 * k + 1)] = be + tg;
     }

@@ -51,6 +51,54 @@ int hostsim_embed(const uint8_t* rgb, uint8_t* out, int h, int w, const uint8_t*
   return 0;
 }
 
+// The product's FAITHFUL mode (k_embed_faithful<.., false>): DCT -> values-only Jacobi -> top column,
+// reconstruction as B + d (C^T u0)(B^T C^T u0 / sigma0)^T - same order of operations as the kernel.
+int hostsim_embed_rank1(const uint8_t* rgb, uint8_t* out, int h, int w, const uint8_t* wm, double alpha,
+                        float* sigma_out, int* sweeps_out) {
+  const int nbh = h / 8, nbw = w / 8;
+  for (size_t p = 0; p < (size_t)h * w; ++p) {
+    float r = unit_from_u8(rgb[3 * p]), g = unit_from_u8(rgb[3 * p + 1]), b = unit_from_u8(rgb[3 * p + 2]);
+    float cb, cr; chroma_exact(r, g, b, cb, cr);
+    uint32_t R, G, B; ycc_to_rgb8_exact(luma_exact(r, g, b), cb, cr, R, G, B);
+    out[3 * p] = (uint8_t)R; out[3 * p + 1] = (uint8_t)G; out[3 * p + 2] = (uint8_t)B;
+  }
+  for (int by = 0; by < nbh; ++by)
+    for (int bx = 0; bx < nbw; ++bx) {
+      float a[64], blk[64], uB[8], vB[8];
+      load_luma(rgb, w, by, bx, a);
+      for (int k = 0; k < 64; ++k) blk[k] = a[k];
+      int sw;
+      const float sig = top_left_vector_faithful(a, uB, &sw);
+      if (sigma_out) sigma_out[by * nbw + bx] = sig;
+      if (sweeps_out) sweeps_out[by * nbw + bx] = sw;
+      const float d = f_add(modulate_sigma0(sig, alpha, wm[by * nbw + bx]), -sig);
+      if (d != 0.0f) {
+        if (sig > 0.0f) {
+          const float inv = f_div(1.0f, sig);
+          for (int j = 0; j < 8; ++j) vB[j] = 0.0f;
+          for (int i = 0; i < 8; ++i)
+            for (int j = 0; j < 8; ++j) vB[j] = fmaf(uB[i], blk[8 * i + j], vB[j]);
+          for (int j = 0; j < 8; ++j) vB[j] = f_mul(vB[j], inv);
+        } else {
+          for (int j = 0; j < 8; ++j) vB[j] = uB[j];
+        }
+        for (int i = 0; i < 8; ++i) {
+          const float du = f_mul(d, uB[i]);
+          for (int j = 0; j < 8; ++j) blk[8 * i + j] = fmaf(du, vB[j], blk[8 * i + j]);
+        }
+      }
+      for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 8; ++j) {
+          size_t p = (size_t)(by * 8 + i) * w + bx * 8 + j;
+          float r = unit_from_u8(rgb[3 * p]), g = unit_from_u8(rgb[3 * p + 1]), b = unit_from_u8(rgb[3 * p + 2]);
+          float cb, cr; chroma_exact(r, g, b, cb, cr);
+          uint32_t R, G, B; ycc_to_rgb8_exact(blk[8 * i + j], cb, cr, R, G, B);
+          out[3 * p] = (uint8_t)R; out[3 * p + 1] = (uint8_t)G; out[3 * p + 2] = (uint8_t)B;
+        }
+    }
+  return 0;
+}
+
 int hostsim_extract(const uint8_t* wmk, const uint8_t* orig, uint8_t* out, int h, int w, double alpha) {
   const int nbh = h / 8, nbw = w / 8;
   for (int by = 0; by < nbh; ++by)

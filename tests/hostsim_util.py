@@ -37,7 +37,9 @@ def embed(rgb, wm, alpha=0.1, mode=0):
     out = np.empty_like(rgb)
     sig = np.zeros(nb, np.float32)
     sw = np.zeros(nb, np.int32)
-    fn = lib().hostsim_embed if mode == 0 else lib().hostsim_embed_fast
+    # mode 0: faithful with the literal U S' Vt product (the library's TMF_MODE_LITERAL); 1: fast;
+    # 3: faithful as the library's default TMF_MODE_FAITHFUL computes it (no V, rank-1 reconstruction)
+    fn = {0: lib().hostsim_embed, 1: lib().hostsim_embed_fast, 3: lib().hostsim_embed_rank1}[mode]
     fn(_p(rgb), _p(out), h, w, _p(wm), C.c_double(alpha), _p(sig), _p(sw))
     return out, sig[: (h // 8) * (w // 8)].reshape(h // 8, w // 8), sw
 
@@ -46,7 +48,7 @@ def extract(a, b, alpha=0.1, mode=0):
     a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
     h, w = a.shape[:2]
     out = np.zeros((h // 8, w // 8), np.uint8)
-    fn = lib().hostsim_extract if mode == 0 else lib().hostsim_extract_fast
+    fn = lib().hostsim_extract_fast if mode == 1 else lib().hostsim_extract
     fn(_p(a), _p(b), _p(out), h, w, C.c_double(alpha))
     return out
 

@@ -9,7 +9,39 @@
 #include "tmf_common.cuh"
 #include "tmf_resize.cuh"
 
+#include <memory>
+#include <mutex>
+
 using namespace tmfi;
+
+namespace {
+// host-side weight tables of one (source, resized) size pair, kept for the next call
+struct TableKey {
+  int src_h, src_w, new_h, new_w;
+  bool operator==(const TableKey& o) const { return src_h == o.src_h && src_w == o.src_w && new_h == o.new_h && new_w == o.new_w; }
+};
+struct HostTables {
+  std::vector<uint8_t> bytes;   // [bounds_h][kT_h][bounds_v][k_v], laid out as in the device workspace
+  int row0 = 0, rows = 0;       // source rows the horizontal pass covers
+};
+std::mutex g_tables_mutex;
+std::vector<std::pair<TableKey, std::shared_ptr<const HostTables>>> g_tables;   // most recent last, at most 8
+
+std::shared_ptr<const HostTables> cached_tables(const TableKey& k) {
+  std::lock_guard<std::mutex> lock(g_tables_mutex);
+  for (auto& e : g_tables)
+    if (e.first == k) return e.second;
+  return nullptr;
+}
+std::shared_ptr<const HostTables> remember_tables(const TableKey& k, std::shared_ptr<const HostTables> t) {
+  std::lock_guard<std::mutex> lock(g_tables_mutex);
+  for (auto& e : g_tables)
+    if (e.first == k) return e.second;          // another thread was faster: same content
+  if (g_tables.size() >= 8) g_tables.erase(g_tables.begin());
+  g_tables.emplace_back(k, t);
+  return t;
+}
+}  // namespace
 
 namespace {
 struct MapPlan {
@@ -83,30 +115,41 @@ int tmf_wm_map_l8(const uint8_t* src, int n, int src_h, int src_w, size_t src_st
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
 
-  // weight tables on the host (libm sin, as Pillow), one upload
-  tmf::AxisTable th, tv;
+  // weight tables on the host (libm sin, as Pillow), one upload.  The tables depend on the four sizes
+  // only and cost ~0.2 ms of sin() per call (most of a single map's latency), so the last few are kept.
   int row0 = 0, rows = src_h;
-  std::vector<uint8_t> host(p.table_bytes, 0);
-  if (p.need_v) {
-    tmf::lanczos_axis_table(src_h, p.g.new_h, tv);
-    if (p.need_h) {  // ImagingResampleInner: the horizontal pass covers only the rows the vertical one reads
-      row0 = tv.bounds[0];
-      rows = tv.bounds[2 * (p.g.new_h - 1)] + tv.bounds[2 * (p.g.new_h - 1) + 1] - row0;
-      for (int i = 0; i < p.g.new_h; ++i) tv.bounds[2 * i] -= row0;
+  const TableKey key{src_h, src_w, p.g.new_h, p.g.new_w};
+  std::shared_ptr<const HostTables> cached = cached_tables(key);
+  if (!cached) {
+    auto t = std::make_shared<HostTables>();
+    tmf::AxisTable th, tv;
+    t->bytes.assign(p.table_bytes, 0);
+    t->rows = src_h;
+    if (p.need_v) {
+      tmf::lanczos_axis_table(src_h, p.g.new_h, tv);
+      if (p.need_h) {  // ImagingResampleInner: the horizontal pass covers only the rows the vertical one reads
+        t->row0 = tv.bounds[0];
+        t->rows = tv.bounds[2 * (p.g.new_h - 1)] + tv.bounds[2 * (p.g.new_h - 1) + 1] - t->row0;
+        for (int i = 0; i < p.g.new_h; ++i) tv.bounds[2 * i] -= t->row0;
+      }
+      memcpy(t->bytes.data() + p.off_bv, tv.bounds.data(), tv.bounds.size() * 4);
+      memcpy(t->bytes.data() + p.off_kv, tv.kk.data(), tv.kk.size() * 4);
     }
-    memcpy(host.data() + p.off_bv, tv.bounds.data(), tv.bounds.size() * 4);
-    memcpy(host.data() + p.off_kv, tv.kk.data(), tv.kk.size() * 4);
+    if (p.need_h) {
+      tmf::lanczos_axis_table(src_w, p.g.new_w, th);
+      memcpy(t->bytes.data() + p.off_bh, th.bounds.data(), th.bounds.size() * 4);
+      int32_t* kT = reinterpret_cast<int32_t*>(t->bytes.data() + p.off_kh);  // tap-major for coalesced loads
+      for (int xx = 0; xx < p.g.new_w; ++xx)
+        for (int i = 0; i < th.ksize; ++i) kT[(size_t)i * p.g.new_w + xx] = th.kk[(size_t)xx * th.ksize + i];
+    }
+    cached = remember_tables(key, t);
   }
-  if (p.need_h) {
-    tmf::lanczos_axis_table(src_w, p.g.new_w, th);
-    memcpy(host.data() + p.off_bh, th.bounds.data(), th.bounds.size() * 4);
-    int32_t* kT = reinterpret_cast<int32_t*>(host.data() + p.off_kh);  // tap-major for coalesced loads
-    for (int xx = 0; xx < p.g.new_w; ++xx)
-      for (int i = 0; i < th.ksize; ++i) kT[(size_t)i * p.g.new_w + xx] = th.kk[(size_t)xx * th.ksize + i];
-  }
+  row0 = cached->row0;
+  rows = cached->rows;
+  const std::vector<uint8_t>& host = cached->bytes;
   if (p.table_bytes > 0) {
     // pageable source: the runtime stages it before returning, so `host` may go out of scope
-    cudaError_t e = cudaMemcpyAsync(ws, host.data(), p.table_bytes, cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaMemcpyAsync(ws, host.data(), p.table_bytes, cudaMemcpyHostToDevice, st);   // (`cached` keeps `host` alive)
     if (e != cudaSuccess) { cudaGetLastError(); return fail(TMF_ERR_CUDA, "weight table upload: %s", cudaGetErrorString(e)); }
   }
   const int32_t* d_bh = reinterpret_cast<const int32_t*>(ws + p.off_bh);

@@ -245,6 +245,7 @@ struct EmbedTileSmem {
 
 struct TileAt {          // warp-uniform: tensor coordinates of the tile's two boxes
   uint32_t c0a, c1a, c2a, c0b, c1b, c2b;
+  uint32_t bxa, bxb;     // first block column of each box (for the map index)
   uint32_t nb;           // 2, or 1 for the last tile of an odd box count
 };
 __device__ __forceinline__ TileAt tile_at(const TileGeom& tg, uint32_t t) {
@@ -255,10 +256,12 @@ __device__ __forceinline__ TileAt tile_at(const TileGeom& tg, uint32_t t) {
   const uint32_t by = fastdiv(r, tg.div_bpr);
   const uint32_t bxb = r - by * tg.boxes_per_row;
   a.c0a = bxb * (uint32_t)kBoxWords; a.c1a = by * 8u; a.c2a = img;
+  a.bxa = bxb * (uint32_t)kBoxBlocks;
   a.nb = (b0 + 1u < tg.total_boxes) ? 2u : 1u;
   const bool same_row = bxb + 1u < tg.boxes_per_row;
   const bool same_img = r + 1u < tg.boxes_per_img;
   a.c0b = same_row ? a.c0a + (uint32_t)kBoxWords : 0u;
+  a.bxb = same_row ? a.bxa + (uint32_t)kBoxBlocks : 0u;
   a.c1b = same_row ? a.c1a : (same_img ? a.c1a + 8u : 0u);
   a.c2b = same_img ? img : img + 1u;
   return a;
@@ -299,10 +302,9 @@ k_embed_tile(const __grid_constant__ CUtensorMap src_map, const __grid_constant_
     if (a.nb == 2u) tma_load_box(tiles_s + kBoxBytes, &src_map, a.c0b, a.c1b, a.c2b, bar);
   };
   auto lane_mark = [&](const TileAt& a) -> uint32_t {  // the lane's watermark value (0 for a missing second box)
-    const uint32_t c0 = half ? a.c0b : a.c0a, c1 = half ? a.c1b : a.c1a, c2 = half ? a.c2b : a.c2a;
+    const uint32_t bx = half ? a.bxb : a.bxa, c1 = half ? a.c1b : a.c1a, c2 = half ? a.c2b : a.c2a;
     if (half && a.nb != 2u) return 0u;
-    const uint32_t bx16 = (c0 * 43691u) >> 18;         // c0 / 6 for c0 < 2^16 ... (c0 = 96 * box column: exact)
-    const uint32_t idx = (c1 >> 3) * tg.nbw + bx16 + l16;
+    const uint32_t idx = (c1 >> 3) * tg.nbw + bx + l16;
     return (uint32_t)__ldg(wm + (wm_shared ? 0u : c2 * tg.blocks_per_img) + idx);
   };
 
@@ -453,13 +455,14 @@ int launch_embed_fast8(const uint8_t* rgb, uint8_t* out, const BlockGeom& g, con
     make_tile_geom(g, tg);
     const int n = (int)(g.total_blocks / g.blocks_per_img);
     CUtensorMap ms, md;
-    if (int rc = make_map(&ms, rgb, g, n)) return rc;
-    if (int rc = make_map(&md, out, g, n)) return rc;
-    const unsigned cap = (unsigned)sm_count() * C;
-    const unsigned need = grid_for(tg.total_tiles, W);
-    kernel<<<need < cap ? need : cap, W * 32, smem, st>>>(ms, md, tg, wm, wm_shared, alpha);
-    g_last_path = 1;
-    return check_launch("embed (tile) kernel launch");
+    if (make_map(&ms, rgb, g, n) == TMF_OK && make_map(&md, out, g, n) == TMF_OK) {
+      const unsigned cap = (unsigned)sm_count() * C;
+      const unsigned need = grid_for(tg.total_tiles, W);
+      kernel<<<need < cap ? need : cap, W * 32, smem, st>>>(ms, md, tg, wm, wm_shared, alpha);
+      g_last_path = 1;
+      return check_launch("embed (tile) kernel launch");
+    }
+    // no tensor maps from this driver (or a shape it refuses): the per-thread kernel computes the same bytes
   }
   const unsigned grid = grid_for(g.total_blocks, kEmbedThreads);
   switch (pick_vec(g, rgb, out)) {

@@ -21,6 +21,7 @@
 namespace tmfi {
 namespace {
 
+constexpr float kTwoM49 = 1.7763568394002505e-15f;     // 2^-49: the quantiser's scaling (tmf_rowmath.cuh), exact
 constexpr int kRowUnroll = TMF_ROW_UNROLL;
 constexpr int kRowUnrollP2 = TMF_ROW_UNROLL_P2;
 constexpr int kEmbedThreads = TMF_EMBED_THREADS;
@@ -103,6 +104,7 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
   // pass 2: the rows again (L1/L2 hits), rank-1 update, colour out, quantise, store
   uint8_t* dst = out + org;
   const float2 w2[4] = {make_float2(w[0], w[1]), make_float2(w[2], w[3]), make_float2(w[4], w[5]), make_float2(w[6], w[7])};
+  const float f49 = f * kTwoM49, c49 = c * kTwoM49;
 #pragma unroll kRowUnrollP2
   for (int i = 0; i < 8; ++i) {
     uint32_t o[6], wd[6];
@@ -110,7 +112,7 @@ k_embed_fast(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGe
     if (mark != 0) { ya = col[(2 * i) * kEmbedThreads]; yb = col[(2 * i + 1) * kEmbedThreads]; }
     load_row24<VEC>(src + (size_t)i * g.row_pitch, wd);
     const float2 y2[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb.x, yb.y), make_float2(yb.z, yb.w)};
-    embed_row_fast2(wd, y2, w2, f, c, o);
+    embed_row_fast2(wd, y2, w2, f49, c49, o);
     store_row24<VEC>(dst + (size_t)i * g.row_pitch, o);
   }
 }
@@ -294,7 +296,9 @@ k_embed_tile(const __grid_constant__ CUtensorMap src_map, const __grid_constant_
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 32; ++k) col[k * kStride] = make_float2(0.0f, 0.0f);   // lanes with a zero mark read their stash as it is:
+  __syncwarp();                                                               // finite values, times f = c = w = 0
 
   auto load_tile = [&](const TileAt& a) {              // by ONE lane: both boxes onto the warp's barrier
     mbar_expect_tx(bar, a.nb * kBoxBytes);
@@ -340,14 +344,15 @@ k_embed_tile(const __grid_constant__ CUtensorMap src_map, const __grid_constant_
     }
     if (valid) {
       const float2 w2[4] = {make_float2(w[0], w[1]), make_float2(w[2], w[3]), make_float2(w[4], w[5]), make_float2(w[6], w[7])};
+      const float f49 = f * kTwoM49, c49 = c * kTwoM49;
 #pragma unroll kRowUnrollP2
       for (int i = 0; i < 8; ++i) {
         uint32_t o[6], wd[6];
         load_row24<0>(mine + i * kBoxRowBytes, wd);
         float2 y2[4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) y2[p] = col[(4 * i + p) * kStride];       // unmarked lanes: stale values, unused
-        embed_row_fast2(wd, y2, w2, f, c, o, mark != 0);
+        for (int p = 0; p < 4; ++p) y2[p] = col[(4 * i + p) * kStride];       // zero-mark lanes: an earlier tile's values, times 0
+        embed_row_fast2(wd, y2, w2, f49, c49, o);
         store_row24<0>(mine + i * kBoxRowBytes, o);
       }
     }

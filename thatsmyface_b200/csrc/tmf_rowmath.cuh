@@ -108,8 +108,8 @@ __device__ __forceinline__ void gram_pairs_to_sym(const GramPairs& G, float (&gm
   }
 }
 
-// Pass 2 for one row, packed: bytes of the row, its luma (4 pairs), w (4 pairs), f, c -> six
-// output words.  Same arithmetic as tmf::embed_row_fast + pack4_sat_u8.
+// Pass 2 for one row, packed: bytes of the row, its luma (4 pairs), w (4 pairs), f * 2^-49, c * 2^-49
+// -> six output words.  Same arithmetic as tmf::embed_row_fast + pack4_sat_u8.
 //
 // The reference maps (r, g, b) to (y, cb, cr), adds the mark to y and maps back with a matrix
 // that is not the exact inverse (watermarking.py:37-39, :61): a pixel comes back as
@@ -124,16 +124,16 @@ __device__ __forceinline__ void gram_pairs_to_sym(const GramPairs& G, float (&gm
 // subnormal too, (r - g) * 2^-149, exact) and in du; power-of-two scalings are exact.
 // Subnormals cost nothing extra in FFMA on this hardware; the build must never use -ftz.
 __device__ __forceinline__ void embed_row_fast2(const uint32_t (&w)[6], const float2 (&y2)[4], const float2 (&w2)[4],
-                                                float f, float c, uint32_t (&o)[6], bool marked = true) {
+                                                float f49, float c49, uint32_t (&o)[6]) {
   float2 acc = __fmul2_rn(y2[0], w2[0]);
 #pragma unroll
   for (int p = 1; p < 4; ++p) acc = __ffma2_rn(y2[p], w2[p], acc);
   // tmf::dot8 accumulates sequentially; the pairwise order differs by rounding only in z,
   // which is scaled by f ~ 1e-3: far below the quantiser's resolution.
-  // `marked` = false: the lane's block has a zero mark, its y2 is whatever the stash held (possibly
-  // not even finite): the update is exactly zero, selected after the arithmetic.
-  float du = fmaf(f, acc.x + acc.y, c) * 1.7763568394002505e-15f;   // * 2^-49 (exact scaling)
-  if (!marked) du = 0.0f;
+  // f49 = f * 2^-49, c49 = c * 2^-49 (scaled once per block by the caller; exact, so du is the same
+  // float as fma(f, z, c) * 2^-49).  A block with a zero mark has f49 = c49 = 0 and w2 = 0: its y2 may be
+  // anything finite (the tile kernel reads stale stash values) and du is exactly 0.
+  const float du = fmaf(f49, acc.x + acc.y, c49);
   int q[24];
 #pragma unroll
   for (int p = 0; p < 4; ++p) {

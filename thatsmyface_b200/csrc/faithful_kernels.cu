@@ -71,7 +71,8 @@ __device__ __forceinline__ void colour_rows_out(const uint8_t* __restrict__ src,
                                                 const float* __restrict__ col) {
 #pragma unroll 1
   for (int i = 0; i < 8; ++i) {
-    uint32_t w[6], o[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t w[6], o[6];
+    int q[24];
     load_row24<VEC>(src + (size_t)i * pitch, w);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -80,12 +81,10 @@ __device__ __forceinline__ void colour_rows_out(const uint8_t* __restrict__ src,
       const float b = unit_of_byte(w, 3 * j + 2);
       float cb, cr;
       tmf::chroma_exact(r, gg, b, cb, cr);
-      uint32_t R, G, B;
-      tmf::ycc_to_rgb8_exact(col[(8 * i + j) * kThreads], cb, cr, R, G, B);
-      o[(3 * j) >> 2] |= R << (8 * ((3 * j) & 3));
-      o[(3 * j + 1) >> 2] |= G << (8 * ((3 * j + 1) & 3));
-      o[(3 * j + 2) >> 2] |= B << (8 * ((3 * j + 2) & 3));
+      tmf::ycc_to_levels_exact(col[(8 * i + j) * kThreads], cb, cr, q[3 * j], q[3 * j + 1], q[3 * j + 2]);
     }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o[k] = tmf::pack4_sat_u8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);   // the clip of :70
     store_row24<VEC>(dst + (size_t)i * pitch, o);
   }
 }
@@ -389,9 +388,10 @@ k_embed_faithful_n(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, B
 #pragma unroll 1
   for (int i = 0; i < N; ++i) {
     uint32_t w[kRowWords<N>], o[kRowWords<N>];
+    int q[4 * kRowWords<N>];
     load_row_n<N, AL>(src + (size_t)i * g.row_pitch, w);
 #pragma unroll
-    for (int k = 0; k < kRowWords<N>; ++k) o[k] = 0;
+    for (int k = 3 * N; k < 4 * kRowWords<N>; ++k) q[k] = 0;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       const float r = unit_of_byte(w, 3 * j);
@@ -399,12 +399,10 @@ k_embed_faithful_n(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, B
       const float b = unit_of_byte(w, 3 * j + 2);
       float cb, cr;
       tmf::chroma_exact(r, gg, b, cb, cr);
-      uint32_t R, G, B;
-      tmf::ycc_to_rgb8_exact(Bm[(i * N + j) * T], cb, cr, R, G, B);
-      o[(3 * j) >> 2] |= R << (8 * ((3 * j) & 3));
-      o[(3 * j + 1) >> 2] |= G << (8 * ((3 * j + 1) & 3));
-      o[(3 * j + 2) >> 2] |= B << (8 * ((3 * j + 2) & 3));
+      tmf::ycc_to_levels_exact(Bm[(i * N + j) * T], cb, cr, q[3 * j], q[3 * j + 1], q[3 * j + 2]);
     }
+#pragma unroll
+    for (int k = 0; k < kRowWords<N>; ++k) o[k] = tmf::pack4_sat_u8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
     store_row_n<N, AL>(dst + (size_t)i * g.row_pitch, o);
   }
 }

@@ -338,20 +338,6 @@ TMF_HD int floor_sum_to_int(float k, float s) {
 #endif
 }
 
-// four floors -> four saturated bytes in one word (byte 0 = a0): two
-// cvt.pack.sat.u8.s32 (SASS I2IP.U8.S32.SAT), each clamps and packs two values.
-TMF_HD uint32_t pack4_sat_u8(int a0, int a1, int a2, int a3) {
-#if defined(__CUDA_ARCH__)
-  uint32_t hi, w;
-  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(a3), "r"(a2), "r"(0));
-  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(a1), "r"(a0), "r"(hi));
-  return w;
-#else
-  auto cl = [](int v) { return (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); };
-  return cl(a0) | (cl(a1) << 8) | (cl(a2) << 16) | (cl(a3) << 24);
-#endif
-}
-
 // pass 2 for one row: r, g, b in 0..255 units and the row's luma y (kept from
 // pass 1) -> 3N output levels q[3j + c] (unclipped floors; pack4_sat_u8 clips)
 template <int N = 8>

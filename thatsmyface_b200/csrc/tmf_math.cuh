@@ -159,33 +159,55 @@ TMF_HD void chroma_exact(float r, float g, float b, float& cb, float& cr) {
   cb = f_add(dot3_npdot(-0.169, -0.331, 0.5, r, g, b), 0.5f);
   cr = f_add(dot3_npdot(0.5, -0.419, -0.081, r, g, b), 0.5f);
 }
-// watermarking.py:58-73: "-= 0.5" in float32, np.dot with Ti, clip, *255 in
-// float32, truncation toward zero.
-TMF_HD void ycc_to_rgb8_exact(float y, float cb, float cr, uint32_t& R, uint32_t& G, uint32_t& B) {
+// watermarking.py:58-73: "-= 0.5" in float32, np.dot with Ti, clip, *255 in float32, truncation
+// toward zero.  ycc_to_levels_exact returns floor(f32(channel * 255)) WITHOUT the clip: the clip
+// commutes with the (monotonic) scaling and floor, clip(floor(255 c), 0, 255) = floor(255 clip(c, 0, 1)),
+// so callers that pack with a saturating instruction (pack4_sat_u8) get it for free - six FMNMX per
+// pixel less; ycc_to_rgb8_exact clips the levels itself.
+TMF_HD void ycc_to_levels_exact(float y, float cb, float cr, int& R, int& G, int& B) {
   float zb = f_add(cb, -0.5f), zr = f_add(cr, -0.5f);
   // np.dot rows (1, 0, 1.403), (1, -0.344, -0.714), (1, 1.773, 0) in dot3_npdot's order
   // acc = t1 x1; acc = fma(t0, x0, acc); acc = fma(t2, x2, acc), with the exact steps folded:
   // 0 * zb = +-0 and fma(1, y, +-0) = y; fma(1, y, acc) = y + acc; fma(0, zr, acc) = acc
   // (identical bits for finite inputs; a NaN / Inf input is garbage in the reference too)
   const double yd = (double)y, zbd = (double)zb, zrd = (double)zr;
-  float r = (float)d_fma(1.403, zrd, yd);
-  float g = (float)d_fma(-0.714, zrd, d_add(yd, d_mul(-0.344, zbd)));
-  float b = (float)d_add(yd, d_mul(1.773, zbd));
-  r = fminf(fmaxf(r, 0.0f), 1.0f);
-  g = fminf(fmaxf(g, 0.0f), 1.0f);
-  b = fminf(fmaxf(b, 0.0f), 1.0f);
+  const float r = (float)d_fma(1.403, zrd, yd);
+  const float g = (float)d_fma(-0.714, zrd, d_add(yd, d_mul(-0.344, zbd)));
+  const float b = (float)d_add(yd, d_mul(1.773, zbd));
 #if defined(__CUDA_ARCH__)
-  // 0 <= x <= 255: truncation == floor, taken with one FADD.RM onto 1.5 * 2^23 and an integer
-  // subtraction instead of F2I (16 lanes/clk/SM)
-  R = (uint32_t)(__float_as_int(__fadd_rd(f_mul(r, 255.0f), 12582912.0f)) - 0x4B400000);
-  G = (uint32_t)(__float_as_int(__fadd_rd(f_mul(g, 255.0f), 12582912.0f)) - 0x4B400000);
-  B = (uint32_t)(__float_as_int(__fadd_rd(f_mul(b, 255.0f), 12582912.0f)) - 0x4B400000);
+  // floor with one FADD.RM onto 1.5 * 2^23 and an integer subtraction instead of F2I (16 lanes/clk/SM);
+  // |255 c| is far below 2^22
+  R = __float_as_int(__fadd_rd(f_mul(r, 255.0f), 12582912.0f)) - 0x4B400000;
+  G = __float_as_int(__fadd_rd(f_mul(g, 255.0f), 12582912.0f)) - 0x4B400000;
+  B = __float_as_int(__fadd_rd(f_mul(b, 255.0f), 12582912.0f)) - 0x4B400000;
 #else
-  R = (uint32_t)f_mul(r, 255.0f);
-  G = (uint32_t)f_mul(g, 255.0f);
-  B = (uint32_t)f_mul(b, 255.0f);
+  R = (int)floorf(f_mul(r, 255.0f));
+  G = (int)floorf(f_mul(g, 255.0f));
+  B = (int)floorf(f_mul(b, 255.0f));
 #endif
 }
+TMF_HD void ycc_to_rgb8_exact(float y, float cb, float cr, uint32_t& R, uint32_t& G, uint32_t& B) {
+  int r, g, b;
+  ycc_to_levels_exact(y, cb, cr, r, g, b);
+  R = (uint32_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+  G = (uint32_t)(g < 0 ? 0 : (g > 255 ? 255 : g));
+  B = (uint32_t)(b < 0 ? 0 : (b > 255 ? 255 : b));
+}
+
+// four floors -> four saturated bytes in one word (byte 0 = a0): two
+// cvt.pack.sat.u8.s32 (SASS I2IP.U8.S32.SAT), each clamps and packs two values.
+TMF_HD uint32_t pack4_sat_u8(int a0, int a1, int a2, int a3) {
+#if defined(__CUDA_ARCH__)
+  uint32_t hi, w;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(a3), "r"(a2), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(a1), "r"(a0), "r"(hi));
+  return w;
+#else
+  auto cl = [](int v) { return (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); };
+  return cl(a0) | (cl(a1) << 8) | (cl(a2) << 16) | (cl(a3) << 24);
+#endif
+}
+
 
 // ---------------------------------------------------------------------------
 // 8-point orthonormal DCT-II / DCT-III on a strided register vector
@@ -306,16 +328,17 @@ TMF_HD float jacobi_cs(float al, float be, float ga, float& c, float& s, float* 
   const float gg = ga * ga;
   const float g2 = ga + ga;
   const bool rot = (gg > (TMF_JACOBI_TOL * TMF_JACOBI_TOL) * ab) && (fminf(al, be) > TMF_JACOBI_FLOOR);
-  // tan of the rotation angle, smaller root: t = 2g / (d + sign(d) sqrt(d^2 + 4g^2))
+  // tan of the rotation angle, smaller root: t = 2g / (d + sign(d) sqrt(d^2 + 4g^2)); forced to 0 for a
+  // pair that is left alone, so that c = 1 and s = 0 fall out of the same arithmetic (no selects)
   const float d = be - al;
   const float r = f_sqrt_fast(fmaf(g2, g2, d * d));
-  const float t = g2 * f_rcp_fast(d + copysignf(r, d));
+  const float t = rot ? g2 * f_rcp_fast(d + copysignf(r, d)) : 0.0f;
   const float tt = fmaf(t, t, 1.0f);
-  float cc = f_rsqrt_fast(tt);                         // tt >= 1
+  float cc = f_rsqrt_fast(tt);                         // tt >= 1 (exactly 1 -> exactly 1)
   cc = fmaf(0.5f * cc, fmaf(-tt * cc, cc, 1.0f), cc);  // one Newton step: c^2 + s^2 = 1 to ~1 ulp
-  c = rot ? cc : 1.0f;
-  s = rot ? cc * t : 0.0f;
-  if (tan_out) *tan_out = rot ? t : 0.0f;
+  c = cc;
+  s = cc * t;
+  if (tan_out) *tan_out = t;
   return rot ? ((gg > (TMF_JACOBI_DONE * TMF_JACOBI_DONE) * ab) ? 2.0f : 1.0f) : 0.0f;
 }
 

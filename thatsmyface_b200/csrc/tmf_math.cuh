@@ -129,17 +129,17 @@ TMF_HD float dot3_npdot(double t0, double t1, double t2, float x0, float x1, flo
 // f32(u8) / 255.0 (below) from the byte already converted to float (callers that extract it from a packed word
 // straight onto the 2^23 magic number)
 TMF_HD float unit_from_float_byte(float k) {
-  const float r = 0.00392156885936856270f;        // RN32(1/255)
-  const float q0 = f_mul(k, r);
-  const float e = fmaf(-q0, 255.0f, k);           // exact residual
-  return fmaf(e, r, q0);
+  // 1/255 = r_hi + r_lo to 48 bits; k * r_hi is exact in the FMA (k has 8 bits), so the result is
+  // k/255 rounded once, off by < 2^-50 relative before that rounding: the correctly rounded quotient
+  // for every byte (all 256 checked with exact rational arithmetic, and by the bit-exact colour tests)
+  const float r_hi = 0.00392156885936856270f;      // RN32(1/255)
+  const float r_lo = -2.319175823606301e-10f;   // RN32(1/255 - r_hi)
+  return fmaf(k, r_hi, f_mul(k, r_lo));
 }
-
-
 // watermarking.py:29 - f32(u8) / 255.0 (IEEE float32 division).  For the 256
-// possible inputs the quotient is reproduced exactly by one FMA-corrected
-// reciprocal step (checked for every byte by tests/test_hostsim.py and by the
-// bit-exact colour taps), which avoids the ~12-instruction division sequence.
+// possible inputs the quotient is reproduced exactly by a two-term reciprocal
+// (checked for every byte by tests/test_hostsim.py and by the bit-exact colour
+// taps), which avoids the ~12-instruction division sequence.
 TMF_HD float unit_from_u8(uint32_t v) {
 #if defined(__CUDA_ARCH__)
   // the byte as a float through the 2^23 magic number (one logic op + one FADD on the full-rate

@@ -14,23 +14,20 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
-def tile(w, c, s, stash, **kw):
-    d = {"TMF_TILE_WARPS": w, "TMF_TILE_CTAS_PER_SM": c, "TMF_TILE_STAGES": s, "TMF_TILE_STASH": stash}
+def tile(w, c, **kw):
+    """Shape of the TMA-tiled embed kernel: warps per CTA (a multiple of 4), CTAs per SM."""
+    d = {"TMF_TILE_WARPS": w, "TMF_TILE_CTAS_PER_SM": c}
     d.update(kw)
     return d
 
 
-def xtile(w, c, s, **kw):
-    d = {"TMF_XTILE_WARPS": w, "TMF_XTILE_CTAS_PER_SM": c, "TMF_XTILE_STAGES": s}
-    d.update(kw)
-    return d
-
-
-VARIANTS = {          # round 2, ninth sweep: tile walk + TMA issue on the uniform datapath (k_embed_tile_u)
+VARIANTS = {          # the knobs that are left (csrc/tmf_tunables.h); earlier sweeps of the round: profiles/r02_sweep_*.txt
     "base": {},
-    "e_uniform": {"TMF_TILE_UNIFORM": 1},
-    "e_uniform_p2u8": {"TMF_TILE_UNIFORM": 1, "TMF_ROW_UNROLL_P2": 8},
-    "e_uniform_p2u2": {"TMF_TILE_UNIFORM": 1, "TMF_ROW_UNROLL_P2": 2},
+    "e_8x2": tile(8, 2),
+    "e_12x1": tile(12, 1),
+    "e_p2u2": {"TMF_ROW_UNROLL_P2": 2},
+    "e_p2u8": {"TMF_ROW_UNROLL_P2": 8},
+    "pt_notile": {},  # per-thread kernels (run with TMF_NO_TILE=1)
 }
 
 

@@ -6,9 +6,9 @@
 // contiguous bytes.  All block arithmetic is in the owning thread's registers with
 // compile-time indices: no shuffles, no exchange between threads, no redundant work.
 //
-//   fast_kernels.cu      FAST mode, block size 8: k_embed_tile / k_extract_tile (TMA-tiled,
-//                        persistent), k_embed_fast / k_extract_fast / k_sigma0_fast (per-thread
-//                        global accesses; any alignment)
+//   fast_kernels.cu      FAST mode, block size 8: k_embed_tile (TMA-tiled, persistent),
+//                        k_embed_fast / k_extract_fast / k_sigma0_fast (per-thread global
+//                        accesses; any alignment)
 //   fast_n_kernels.cu    FAST mode, the UI's other block sizes (4..16)
 //   faithful_kernels.cu  FAITHFUL mode (DCT -> one-sided Jacobi -> IDCT), every block size
 //   taps.cu              svd / dct / colour / pixel-format taps, strip round trip

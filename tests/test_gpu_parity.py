@@ -478,7 +478,9 @@ def test_literal_mode_is_block_8_only():
 @pytest.mark.parametrize("bs", [4, 6, 10, 12, 14, 16])
 def test_other_block_sizes_vs_oracle(bs, mode):
     rng = np.random.default_rng(bs)
-    for (h, w) in ((7 * bs + 1, 9 * bs + 3), (16 * bs, 24 * bs)):          # ragged / aligned
+    # ragged (byte path) / aligned, even block count per row / 4-byte rows with an ODD block count per row (the
+    # aligned-word path of sizes 6, 10, 14 with unpaired lanes at the row ends: 9 bs + 2 is a multiple of 4 for them)
+    for (h, w) in ((7 * bs + 1, 9 * bs + 3), (16 * bs, 24 * bs), (5 * bs + 3, 9 * bs + 2)):
         img = natural_like(h, w, bs)
         wm = np.where(rng.random((h // bs, w // bs)) < 0.4, 0, rng.integers(1, 256, (h // bs, w // bs))).astype(np.uint8)
         ref = O.embed_array(img, wm, 0.1, bs)
@@ -491,9 +493,9 @@ def test_other_block_sizes_vs_oracle(bs, mode):
         Y = O.rgb_to_ycbcr(img)[:, :, 0]
         sref = np.linalg.svd(O.to_blocks(Y, bs).astype(np.float64), compute_uv=False)[..., 0]
         assert (np.abs(s0 - sref) <= SIGMA_RTOL * sref + 1e-12).all()
-    # batch path with per-image maps
-    imgs = np.stack([natural_like(4 * bs, 6 * bs, k) for k in range(3)])
-    wms = rng.integers(0, 256, (3, 4, 6), dtype=np.uint8)
+    # batch path with per-image maps (3 x 5 blocks per image: block parity and lane parity drift apart across images)
+    imgs = np.stack([natural_like(3 * bs, 5 * bs + 2, k) for k in range(3)])
+    wms = rng.integers(0, 256, (3, 3, 5), dtype=np.uint8)
     got = W.embed_watermark_batch(imgs, wms, 0.1, bs, mode)
     for k in range(3):
         assert np.abs(got[k].astype(int) - O.embed_array(imgs[k], wms[k], 0.1, bs).astype(int)).max() <= 1

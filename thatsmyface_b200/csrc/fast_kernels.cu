@@ -256,11 +256,11 @@ __device__ __forceinline__ TileAt tile_at(const TileGeom& tg, uint32_t t) {
   const uint32_t img = fastdiv(b0, tg.div_bpi);
   const uint32_t r = b0 - img * tg.boxes_per_img;
   const uint32_t by = fastdiv(r, tg.div_bpr);
-  const uint32_t bxb = r - by * tg.boxes_per_row;
-  a.c0a = bxb * (uint32_t)kBoxWords; a.c1a = by * 8u; a.c2a = img;
-  a.bxa = bxb * (uint32_t)kBoxBlocks;
+  const uint32_t bcol = r - by * tg.boxes_per_row;      // box column inside the block-row
+  a.c0a = bcol * (uint32_t)kBoxWords; a.c1a = by * 8u; a.c2a = img;
+  a.bxa = bcol * (uint32_t)kBoxBlocks;
   a.nb = (b0 + 1u < tg.total_boxes) ? 2u : 1u;
-  const bool same_row = bxb + 1u < tg.boxes_per_row;
+  const bool same_row = bcol + 1u < tg.boxes_per_row;
   const bool same_img = r + 1u < tg.boxes_per_img;
   a.c0b = same_row ? a.c0a + (uint32_t)kBoxWords : 0u;
   a.bxb = same_row ? a.bxa + (uint32_t)kBoxBlocks : 0u;

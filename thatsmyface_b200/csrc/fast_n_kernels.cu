@@ -10,7 +10,8 @@
 // extraction), and pass 2 floors straight onto the integer level with the subnormal
 // quantiser (tmf_rowmath.cuh).
 //
-// Access width AL.  4: block rows start 4-byte aligned (3N % 4 == 0: N = 4, 12, 16).  3: sizes with
+// Access width AL.  16: N = 16 with 16-byte aligned rows (three LDG.128 / STG.128 per 48-byte block row
+// instead of twelve 32-bit accesses).  4: block rows start 4-byte aligned (3N % 4 == 0: N = 4, 12, 16).  3: sizes with
 // 3N % 4 == 2 (N = 6, 10, 14) in rows that start 4-byte aligned: blocks alternate between offsets
 // 0 and 2 (mod 4) along a row, so every lane reads the aligned words that cover its row and
 // funnel-shifts by 0 or 16 bits, and writes aligned words too - the one word an even block shares
@@ -30,7 +31,14 @@ namespace {
 // ---- row I/O: AL = 3 is the aligned-words-with-parity path, the others are tmf_common.cuh's ----
 template <int N, int AL>
 __device__ __forceinline__ void load_row(const uint8_t* __restrict__ p, bool odd, uint32_t (&w)[kRowWords<N>]) {
-  if (AL == 3) {
+  if (AL == 16) {                       // N = 16: a block row is 48 bytes = three 16-byte words
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int k = 0; k < (3 * N) / 16; ++k) {
+      const uint4 v = __ldg(q + k);
+      w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+    }
+  } else if (AL == 3) {
     constexpr int NW = kRowWords<N>;
     const uint32_t* q = reinterpret_cast<const uint32_t*>(p - (odd ? 2 : 0));
     const uint32_t sh = odd ? 16u : 0u;
@@ -41,13 +49,17 @@ __device__ __forceinline__ void load_row(const uint8_t* __restrict__ p, bool odd
     for (int k = 0; k < NW - 1; ++k) w[k] = __funnelshift_r(r[k], r[k + 1], sh);
     w[NW - 1] = r[NW - 1] >> sh;          // even lanes: the upper half is the neighbour's (never used)
   } else {
-    load_row_n<N, (AL == 3 ? 2 : AL)>(p, w);
+    load_row_n<N, (AL == 3 || AL == 16 ? 2 : AL)>(p, w);
   }
 }
 
 template <int N, int AL>
 __device__ __forceinline__ void store_row(uint8_t* __restrict__ p, bool odd, bool paired, const uint32_t (&o)[kRowWords<N>]) {
-  if (AL == 3) {
+  if (AL == 16) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int k = 0; k < (3 * N) / 16; ++k) q[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+  } else if (AL == 3) {
     constexpr int NW = kRowWords<N>;
     // The word an even block shares with its right-hand neighbour is completed with a shuffle and
     // written by the even lane.  `paired`: that neighbour is the next lane (same warp, same row) for an
@@ -65,7 +77,7 @@ __device__ __forceinline__ void store_row(uint8_t* __restrict__ p, bool odd, boo
       *reinterpret_cast<uint16_t*>(p) = (uint16_t)o[0];
     }
   } else {
-    store_row_n<N, (AL == 3 ? 2 : AL)>(p, o);
+    store_row_n<N, (AL == 3 || AL == 16 ? 2 : AL)>(p, o);
   }
 }
 
@@ -232,24 +244,31 @@ k_sigma0_fast_n(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, Blo
 // A = access width the block rows allow (4 needs 3N % 4 == 0 || the trailing halfword: any even N
 // has 3N % 2 == 0, so rows that start 4-byte aligned can use word loads plus one halfword).
 template <int N, typename F>
-void with_access_width(int al, bool, F&& f) {
+void with_access_width(int al, bool all16, F&& f) {
+  if constexpr (N == 16) {
+    if (all16) { f(std::integral_constant<int, N>{}, std::integral_constant<int, 16>{}); return; }
+  }
   if (al == 4 && (3 * N) % 4 == 0) f(std::integral_constant<int, N>{}, std::integral_constant<int, 4>{});
   else if (al == 4) f(std::integral_constant<int, N>{}, std::integral_constant<int, 3>{});
   else if (al >= 2) f(std::integral_constant<int, N>{}, std::integral_constant<int, 2>{});
   else f(std::integral_constant<int, N>{}, std::integral_constant<int, 1>{});
 }
 template <typename F>
-void for_block_size(const BlockGeom& g, int al, F&& f) {
-  const bool even_rows = (g.nbw & 1) == 0;      // AL = 3: blocks pair up inside every row
+void for_block_size(const BlockGeom& g, int al, F&& f, bool even_rows) {
   switch (g.bs) {
-    case 4: with_access_width<4>(al, even_rows, f); break;
-    case 6: with_access_width<6>(al, even_rows, f); break;
-    case 10: with_access_width<10>(al, even_rows, f); break;
-    case 12: with_access_width<12>(al, even_rows, f); break;
-    case 14: with_access_width<14>(al, even_rows, f); break;
+    case 4: with_access_width<4>(al, false, f); break;
+    case 6: with_access_width<6>(al, false, f); break;
+    case 10: with_access_width<10>(al, false, f); break;
+    case 12: with_access_width<12>(al, false, f); break;
+    case 14: with_access_width<14>(al, false, f); break;
     case 16: with_access_width<16>(al, even_rows, f); break;
     default: break;
   }
+}
+
+// pointers, image stride and row pitch all multiples of 16 (block rows of N = 16 then are, too)
+bool all16(const BlockGeom& g, const void* p0, const void* p1) {
+  return (((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)g.img_stride | (uintptr_t)g.row_pitch) & 15) == 0;
 }
 
 }  // namespace
@@ -259,7 +278,7 @@ int launch_embed_fast_n(const uint8_t* rgb, uint8_t* out, const BlockGeom& g, co
   const unsigned grid = grid_for(g.total_blocks, kThreads);
   for_block_size(g, row_alignment(g, rgb, out), [&](auto n_, auto a_) {
     k_embed_fast_n<decltype(n_)::value, decltype(a_)::value><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha);
-  });
+  }, all16(g, rgb, out));
   return check_launch("embed kernel launch");
 }
 
@@ -268,7 +287,7 @@ int launch_extract_fast_n(const uint8_t* wmk, const uint8_t* orig, uint8_t* out_
   const unsigned grid = grid_for(g.total_blocks, kThreads);
   for_block_size(g, row_alignment(g, wmk, orig), [&](auto n_, auto a_) {
     k_extract_fast_n<decltype(n_)::value, decltype(a_)::value><<<grid, kThreads, 0, st>>>(wmk, orig, out_wm, g, alpha);
-  });
+  }, all16(g, wmk, orig));
   return check_launch("extract kernel launch");
 }
 
@@ -276,7 +295,7 @@ int launch_sigma0_fast_n(const uint8_t* rgb, float* sigma0, const BlockGeom& g, 
   const unsigned grid = grid_for(g.total_blocks, kThreads);
   for_block_size(g, row_alignment(g, rgb, rgb), [&](auto n_, auto a_) {
     k_sigma0_fast_n<decltype(n_)::value, decltype(a_)::value><<<grid, kThreads, 0, st>>>(rgb, sigma0, g);
-  });
+  }, all16(g, rgb, rgb));
   return check_launch("sigma0 kernel launch");
 }
 

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define TMF_VERSION 100 /* 0.1.0 */
+#define TMF_VERSION 200 /* 0.2.0: TMF_MODE_LITERAL, tmf_last_fast_path, faithful mode at every block size */
 
 enum {
   TMF_OK = 0,

@@ -139,6 +139,11 @@ size_t tmf_wm_map_workspace_bytes(int n, int src_h, int src_w, int target_h, int
 int tmf_wm_map_l8(const uint8_t* src, int n, int src_h, int src_w, size_t src_stride, uint8_t* maps, int target_h,
                   int target_w, int preserve_ratio, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Host only, no device needed: the weight table of one resampling axis as the kernels receive it
+ * (Resample.c precompute_coeffs + normalize_coeffs_8bpc): ksize, bounds = out_size x {first, count},
+ * kk = out_size x ksize 22-bit fixed-point weights.  bounds == kk == NULL queries ksize only. */
+int tmf_wm_map_axis_table(int in_size, int out_size, int* ksize, int32_t* bounds, int32_t* kk, size_t kk_capacity);
+
 /* ---- host-buffer pipeline -------------------------------------------------------------
  * The per-image loop of the embed page (embed_watermark_page.py:492-558) as one call on
  * HOST memory.  A context owns 3 streams and `depth` device slots on one device; the

@@ -103,6 +103,51 @@ def test_tall_sources_take_pillows_vertical_first_path():
     assert np.array_equal(PL.resize_l8(src, 40, 3), ref)
 
 
+def product_axis_table(in_size, out_size):
+    """The PRODUCT library's own host table (tmf_wm_map_axis_table: host only, no device touched)."""
+    import ctypes as C
+
+    from thatsmyface_b200 import _lib
+    lib = _lib.load()
+    ks = C.c_int(0)
+    assert lib.tmf_wm_map_axis_table(in_size, out_size, C.byref(ks), None, None, 0) == 0
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ks.value), np.int32)
+    assert lib.tmf_wm_map_axis_table(in_size, out_size, C.byref(ks), bounds.ctypes.data, kk.ctypes.data, kk.size) == 0
+    return ks.value, bounds, kk
+
+
+@pytest.mark.parametrize("in_size,out_size", [(290, 240), (290, 135), (370, 64), (1000, 7), (33, 240), (8, 8), (49136, 5),
+                                              (777, 270), (1, 3), (3, 1), (4096, 480)])
+def test_product_library_host_tables_equal_pillows(in_size, out_size):
+    """libtmfwm.so's host floating point (libm sin, float64 weights rounded to 22-bit fixed point,
+    built with -ffp-contract=off) must give Pillow's tables bit for bit - checked on the shipped .so, not on
+    the hostsim build.  The restatement it is compared with is pinned to Pillow above; the second half asks
+    Pillow directly: a one-row image through the tables equals Image.resize."""
+    ks, bounds, kk = product_axis_table(in_size, out_size)
+    ks_o, bounds_o, kk_o = PL.precompute_coeffs(in_size, out_size)
+    assert ks == ks_o
+    assert np.array_equal(bounds, bounds_o)
+    assert np.array_equal(kk, kk_o)
+    rng = np.random.default_rng(in_size * 31 + out_size)
+    row = rng.integers(0, 256, (1, in_size), dtype=np.uint8)
+    acc = np.array([(row[0, b0:b0 + n].astype(np.int64) * kk[i, :n]).sum() for i, (b0, n) in enumerate(bounds)])
+    mine = np.clip((acc + (1 << (PL.PRECISION_BITS - 1))) >> PL.PRECISION_BITS, 0, 255).astype(np.uint8)
+    pil = np.array(Image.fromarray(row, "L").resize((out_size, 1), Image.LANCZOS))[0]
+    assert np.array_equal(mine, pil)
+
+
+def test_axis_table_rejects_bad_sizes():
+    import ctypes as C
+
+    from thatsmyface_b200 import _lib
+    lib = _lib.load()
+    ks = C.c_int(0)
+    assert lib.tmf_wm_map_axis_table(0, 4, C.byref(ks), None, None, 0) == _lib.ERR_BAD_ARG
+    small = np.zeros(4, np.int32)
+    assert lib.tmf_wm_map_axis_table(100, 10, C.byref(ks), small.ctypes.data, small.ctypes.data, 4) == _lib.ERR_BAD_ARG
+
+
 # ----------------------------------------------------------------------------- GPU
 torch = pytest.importorskip("torch")
 

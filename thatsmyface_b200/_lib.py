@@ -28,6 +28,7 @@ PROTOTYPES = {
     "tmf_rgbx8_to_rgb8": (_i, [_vp, _vp, _i64, _vp]),
     "tmf_rgb8_to_rgbx8": (_i, [_vp, _vp, _i64, _i, _vp]),
     "tmf_wm_map_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "tmf_wm_map_axis_table": (_i, [_i, _i, _vp, _vp, _vp, _sz]),
     "tmf_wm_map_l8": (_i, [_vp, _i, _i, _i, _sz, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "tmf_ctx_create": (_i, [C.POINTER(_vp), _i, _sz, _i]),
     "tmf_ctx_destroy": (_i, [_vp]),

@@ -102,6 +102,20 @@ size_t tmf_wm_map_workspace_bytes(int n, int src_h, int src_w, int target_h, int
   return p.total_bytes > 0 ? p.total_bytes : 16;
 }
 
+// Host only (no device is touched): the weight table of one axis, as the kernels get it.  A GPU-free pin of this
+// library's host floating point (libm sin, -ffp-contract=off) against Pillow's tables.
+int tmf_wm_map_axis_table(int in_size, int out_size, int* ksize, int32_t* bounds, int32_t* kk, size_t kk_capacity) {
+  if (in_size < 1 || out_size < 1 || !ksize) return fail(TMF_ERR_BAD_ARG, "axis table: sizes must be positive");
+  tmf::AxisTable t;
+  tmf::lanczos_axis_table(in_size, out_size, t);
+  *ksize = t.ksize;
+  if (!bounds && !kk) return TMF_OK;                      // size query
+  if (!bounds || !kk || kk_capacity < t.kk.size()) return fail(TMF_ERR_BAD_ARG, "axis table: %zu coefficients needed", t.kk.size());
+  memcpy(bounds, t.bounds.data(), t.bounds.size() * sizeof(int32_t));
+  memcpy(kk, t.kk.data(), t.kk.size() * sizeof(int32_t));
+  return TMF_OK;
+}
+
 int tmf_wm_map_l8(const uint8_t* src, int n, int src_h, int src_w, size_t src_stride, uint8_t* maps, int target_h,
                   int target_w, int preserve_ratio, void* workspace, size_t workspace_bytes, void* stream) {
   MapPlan p;

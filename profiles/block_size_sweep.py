@@ -5,7 +5,7 @@ from thatsmyface_b200 import watermarking as W
 n=64
 imgs=torch.empty((n,bench.H,bench.W,3),dtype=torch.uint8,device='cuda'); bench.fill_images_device(imgs,0,17)
 out=torch.empty_like(imgs)
-for bs in (4,6,8,10,12,14,16):
+for bs in ([int(a) for a in sys.argv[1:]] or (4,6,8,10,12,14,16)):
     wm=(torch.rand((bench.H//bs,bench.W//bs),device='cuda')<0.5).to(torch.uint8)*255
     for _ in range(2): W.embed_tensor(imgs,wm,0.1,bs,1,out=out)
     e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)

@@ -1,0 +1,36 @@
+"""Tuning variants of the generic-N fast kernels (csrc/fast_n_kernels.cu), timed with block_size_sweep.py.
+
+    python profiles/sweep_block_size_variants.py build      (build container)
+    python profiles/sweep_block_size_variants.py run        (GPU box)
+"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
+VARIANTS = {
+    "fn_default": {},
+    "fn_noahead": {"TMF_FASTN_ROWS_AHEAD_MAX_N": 0},
+    "fn_ahead16": {"TMF_FASTN_ROWS_AHEAD_MAX_N": 16},
+    "fn_ahead16_large2": {"TMF_FASTN_ROWS_AHEAD_MAX_N": 16, "TMF_FASTN_CTAS_LARGE": 2},
+    "fn_large2": {"TMF_FASTN_CTAS_LARGE": 2},
+    "fn_12c2_10c3": {"TMF_FASTN_CTAS_12": 2, "TMF_FASTN_CTAS_10": 3},
+    "fn_small8_10c5": {"TMF_FASTN_CTAS_SMALL": 8, "TMF_FASTN_CTAS_10": 5},
+}
+SIZES = ["4", "6", "10", "12", "14", "16"]
+
+if sys.argv[1] == "build":
+    from thatsmyface_b200 import build as b
+    os.makedirs(VDIR, exist_ok=True)
+    for name, defs in VARIANTS.items():
+        b.build(defines=[f"{k}={v}" for k, v in defs.items()], out=os.path.join(VDIR, f"libtmfwm_{name}.so"))
+        print(name, "ok", flush=True)
+else:
+    for name in VARIANTS:
+        env = dict(os.environ, TMF_LIBPATH=os.path.join(VDIR, f"libtmfwm_{name}.so"))
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "block_size_sweep.py")] + SIZES, env=env,
+                           capture_output=True, text=True, timeout=600)
+        print(f"== {name} {VARIANTS[name]}", flush=True)
+        print(r.stdout.strip() if r.returncode == 0 else "FAILED\n" + r.stderr[-1500:], flush=True)

@@ -29,27 +29,36 @@ namespace tmfi {
 namespace {
 
 // ---- row I/O: AL = 3 is the aligned-words-with-parity path, the others are tmf_common.cuh's ----
+// load_row = fetch_row (the loads, nothing that waits for them) + settle_row (the parity shift of AL = 3): the row
+// loops fetch row i + 1 before they work on row i, so the split keeps the shift from dragging the wait forward.
 template <int N, int AL>
-__device__ __forceinline__ void load_row(const uint8_t* __restrict__ p, bool odd, uint32_t (&w)[kRowWords<N>]) {
+__device__ __forceinline__ void fetch_row(const uint8_t* __restrict__ p, bool odd, uint32_t (&r)[kRowWords<N>]) {
   if (AL == 16) {                       // N = 16: a block row is 48 bytes = three 16-byte words
     const uint4* q = reinterpret_cast<const uint4*>(p);
 #pragma unroll
     for (int k = 0; k < (3 * N) / 16; ++k) {
       const uint4 v = __ldg(q + k);
-      w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+      r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
     }
   } else if (AL == 3) {
-    constexpr int NW = kRowWords<N>;
     const uint32_t* q = reinterpret_cast<const uint32_t*>(p - (odd ? 2 : 0));
-    const uint32_t sh = odd ? 16u : 0u;
-    uint32_t r[NW];
 #pragma unroll
-    for (int k = 0; k < NW; ++k) r[k] = __ldg(q + k);
+    for (int k = 0; k < kRowWords<N>; ++k) r[k] = __ldg(q + k);
+  } else {
+    load_row_n<N, (AL == 3 || AL == 16 ? 2 : AL)>(p, r);
+  }
+}
+template <int N, int AL>
+__device__ __forceinline__ void settle_row(bool odd, const uint32_t (&r)[kRowWords<N>], uint32_t (&w)[kRowWords<N>]) {
+  constexpr int NW = kRowWords<N>;
+  if (AL == 3) {
+    const uint32_t sh = odd ? 16u : 0u;
 #pragma unroll
     for (int k = 0; k < NW - 1; ++k) w[k] = __funnelshift_r(r[k], r[k + 1], sh);
     w[NW - 1] = r[NW - 1] >> sh;          // even lanes: the upper half is the neighbour's (never used)
   } else {
-    load_row_n<N, (AL == 3 || AL == 16 ? 2 : AL)>(p, w);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) w[k] = r[k];
   }
 }
 
@@ -117,17 +126,41 @@ __device__ __forceinline__ float byte_subnormal_n(const uint32_t (&w)[NW], int B
   return __uint_as_float(m);
 }
 
+// Row loops fetch one row ahead (ping-pong, two rows per trip) where the extra row of registers does not spill.
+template <int N> constexpr bool kRowsAhead = N <= TMF_FASTN_ROWS_AHEAD_MAX_N;
+
+template <int N, int AL>
+__device__ __forceinline__ void gram_row_n(bool odd, const uint32_t (&r)[kRowWords<N>], float* gm) {
+  uint32_t w[kRowWords<N>];
+  float y[N];
+  settle_row<N, AL>(odd, r, w);
+  row_luma_n<N>(w, y);
+  tmf::gram_accumulate_row<N>(y, gm);
+}
+
+// Rows two at a time, ping-pong: the loads of the next row are in flight while this one is worked on (one
+// thread per block leaves few warps per SM - 16-23 % occupancy - so the latency has to be covered in the thread).
 template <int N, int AL>
 __device__ __forceinline__ void gram_of_block_n(const uint8_t* __restrict__ base, size_t pitch, bool odd, float* gm) {
 #pragma unroll
   for (int k = 0; k < N * (N + 1) / 2; ++k) gm[k] = 0.0f;
+  uint32_t ra[kRowWords<N>];
+  if constexpr (kRowsAhead<N>) {
+    uint32_t rb[kRowWords<N>];
+    fetch_row<N, AL>(base, odd, ra);
 #pragma unroll 1
-  for (int i = 0; i < N; ++i) {
-    uint32_t w[kRowWords<N>];
-    float y[N];
-    load_row<N, AL>(base + (size_t)i * pitch, odd, w);
-    row_luma_n<N>(w, y);
-    tmf::gram_accumulate_row<N>(y, gm);
+    for (int i = 0; i < N; i += 2) {
+      fetch_row<N, AL>(base + (size_t)(i + 1) * pitch, odd, rb);
+      gram_row_n<N, AL>(odd, ra, gm);
+      if (i + 2 < N) fetch_row<N, AL>(base + (size_t)(i + 2) * pitch, odd, ra);
+      gram_row_n<N, AL>(odd, rb, gm);
+    }
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) {
+      fetch_row<N, AL>(base + (size_t)i * pitch, odd, ra);
+      gram_row_n<N, AL>(odd, ra, gm);
+    }
   }
 }
 
@@ -195,12 +228,31 @@ k_embed_fast_n(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, Block
     gram_of_block_n<N, AL>(src, g.row_pitch, odd, gm);
     tmf::embed_block_scalars_fast<N>(gm, alpha, mark, w, f, c, nullptr, TMF_LUMA_UNIT);
   }
+  uint32_t ra[kRowWords<N>];
+  if constexpr (kRowsAhead<N>) {
+    uint32_t rb[kRowWords<N>];
+    fetch_row<N, AL>(src, odd, ra);
 #pragma unroll 1
-  for (int i = 0; i < N; ++i) {
-    uint32_t wd[kRowWords<N>], o[kRowWords<N>];
-    load_row<N, AL>(src + (size_t)i * g.row_pitch, odd, wd);
-    embed_row_n<N>(wd, w, f, c, mark != 0, o);
-    store_row<N, AL>(dst + (size_t)i * g.row_pitch, odd, paired, o);
+    for (int i = 0; i < N; i += 2) {
+      uint32_t wd[kRowWords<N>], o[kRowWords<N>];
+      fetch_row<N, AL>(src + (size_t)(i + 1) * g.row_pitch, odd, rb);
+      settle_row<N, AL>(odd, ra, wd);
+      embed_row_n<N>(wd, w, f, c, mark != 0, o);
+      store_row<N, AL>(dst + (size_t)i * g.row_pitch, odd, paired, o);
+      if (i + 2 < N) fetch_row<N, AL>(src + (size_t)(i + 2) * g.row_pitch, odd, ra);
+      settle_row<N, AL>(odd, rb, wd);
+      embed_row_n<N>(wd, w, f, c, mark != 0, o);
+      store_row<N, AL>(dst + (size_t)(i + 1) * g.row_pitch, odd, paired, o);
+    }
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) {
+      uint32_t wd[kRowWords<N>], o[kRowWords<N>];
+      fetch_row<N, AL>(src + (size_t)i * g.row_pitch, odd, ra);
+      settle_row<N, AL>(odd, ra, wd);
+      embed_row_n<N>(wd, w, f, c, mark != 0, o);
+      store_row<N, AL>(dst + (size_t)i * g.row_pitch, odd, paired, o);
+    }
   }
 }
 

@@ -127,7 +127,8 @@ TMF_HD float sym_frob2(const float* m) {
   for (int i = 0; i < N; ++i) {
     d = fmaf(m[sym_idx<N>(i, i)], m[sym_idx<N>(i, i)], d);
 #pragma unroll
-    for (int j = i + 1; j < N; ++j) o = fmaf(m[sym_idx<N>(i, j)], m[sym_idx<N>(i, j)], o);
+    for (int j = 0; j < N; ++j)          // fixed trip count: a `j = i + 1` start is left rolled for N >= 10, and the
+      if (j > i) o = fmaf(m[sym_idx<N>(i, j)], m[sym_idx<N>(i, j)], o);   // dynamic index then pins m[] to local memory
   }
   return fmaf(2.0f, o, d);
 }

@@ -58,5 +58,9 @@
 #define TMF_FASTN_CTAS_12 3
 #endif
 #ifndef TMF_FASTN_CTAS_LARGE
-#define TMF_FASTN_CTAS_LARGE 3
+#define TMF_FASTN_CTAS_LARGE 2     // 255 registers: the 105 / 136-entry Gram matrix, a row ahead, no spill
+#endif
+// ... and the largest block size whose row loops fetch one row ahead (a second row of registers)
+#ifndef TMF_FASTN_ROWS_AHEAD_MAX_N
+#define TMF_FASTN_ROWS_AHEAD_MAX_N 16
 #endif

@@ -10,14 +10,11 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
-VARIANTS = {
+VARIANTS = {          # earlier tables: r02_sweep_j_block_sizes.txt (rows ahead, CTAs per SM), r02_sweep_l (packed Gram)
     "fn_default": {},
-    "fn_noahead": {"TMF_FASTN_ROWS_AHEAD_MAX_N": 0},
-    "fn_ahead16": {"TMF_FASTN_ROWS_AHEAD_MAX_N": 16},
-    "fn_ahead16_large2": {"TMF_FASTN_ROWS_AHEAD_MAX_N": 16, "TMF_FASTN_CTAS_LARGE": 2},
-    "fn_large2": {"TMF_FASTN_CTAS_LARGE": 2},
-    "fn_12c2_10c3": {"TMF_FASTN_CTAS_12": 2, "TMF_FASTN_CTAS_10": 3},
-    "fn_small8_10c5": {"TMF_FASTN_CTAS_SMALL": 8, "TMF_FASTN_CTAS_10": 5},
+    "fn_14c2": {"TMF_FASTN_CTAS_14": 2},
+    "fn_16c3": {"TMF_FASTN_CTAS_16": 3},
+    "fn_12c2": {"TMF_FASTN_CTAS_12": 2},
 }
 SIZES = ["4", "6", "10", "12", "14", "16"]
 

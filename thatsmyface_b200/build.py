@@ -12,6 +12,7 @@ from __future__ import annotations
 import glob
 import hashlib
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -61,10 +62,22 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
+def _closure(path: str, seen: list | None = None) -> list:
+    """`path` and the project headers it includes, transitively (csrc/ and include/)."""
+    seen = [] if seen is None else seen
+    if path in seen or not os.path.isfile(path):
+        return seen
+    seen.append(path)
+    for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', open(path).read(), flags=re.M):
+        for base in (CSRC, os.path.join(ROOT, "include")):
+            _closure(os.path.join(base, inc), seen)
+    return seen
+
+
 def _key(src: str, flags) -> str:
     h = hashlib.sha256()
     h.update(" ".join(flags).encode())
-    for p in [os.path.join(CSRC, src)] + _headers():
+    for p in _closure(os.path.join(CSRC, src)):
         with open(p, "rb") as f:
             h.update(p.encode())
             h.update(f.read())
@@ -78,12 +91,10 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
     os.makedirs(os.path.dirname(out), exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     nvcc = _nvcc()
-    # a -D override of a tunable matters only to the translation units that use it (the tunables
-    # header itself merely supplies defaults): the others keep their cached objects
-    other_headers = "".join(open(h).read() for h in _headers() if not h.endswith("tmf_tunables.h"))
-
+    # a -D override of a tunable matters only to the translation units that use it, in their own text or in a
+    # header they include (the tunables header itself merely supplies defaults): the others keep their objects
     def flags_for(src: str):
-        text = open(os.path.join(CSRC, src)).read() + other_headers
+        text = "".join(open(p).read() for p in _closure(os.path.join(CSRC, src)) if not p.endswith("tmf_tunables.h"))
         used = [d for d in defines if d.split("=")[0] in text]
         return NVCC_FLAGS + [f"-D{d}" for d in used] + (["-Xptxas", "-v"] if verbose else [])
 

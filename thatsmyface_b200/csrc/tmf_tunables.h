@@ -47,7 +47,7 @@
 #endif
 
 // generic-N fast kernels (fast_n_kernels.cu): minimum CTAs of 128 threads per SM by block size
-// (4, 6 | 10 | 12 | 14, 16); the Gram matrix alone is N (N + 1) / 2 registers
+// (4, 6 | 10 | 12 | 14 | 16); the Gram matrix alone is N (N + 1) / 2 registers
 #ifndef TMF_FASTN_CTAS_SMALL
 #define TMF_FASTN_CTAS_SMALL 6
 #endif
@@ -57,8 +57,11 @@
 #ifndef TMF_FASTN_CTAS_12
 #define TMF_FASTN_CTAS_12 3
 #endif
-#ifndef TMF_FASTN_CTAS_LARGE
-#define TMF_FASTN_CTAS_LARGE 2     // 255 registers: the 105 / 136-entry Gram matrix, a row ahead, no spill
+#ifndef TMF_FASTN_CTAS_14
+#define TMF_FASTN_CTAS_14 3        // 168 registers: a few spilled words, but 12 warps per SM (extract 557 k -> 621 k MP/s)
+#endif
+#ifndef TMF_FASTN_CTAS_16
+#define TMF_FASTN_CTAS_16 2        // 255 registers: the 136-entry Gram matrix and a row ahead, no spill (3 spills 1 KB: 0.68x)
 #endif
 // ... and the largest block size whose row loops fetch one row ahead (a second row of registers)
 #ifndef TMF_FASTN_ROWS_AHEAD_MAX_N

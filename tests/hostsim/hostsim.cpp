@@ -271,6 +271,17 @@ int hostsim_svd(const float* blocks, int64_t n, float* AV, float* V, float* S, i
   return 0;
 }
 
+// top singular triplet's left half of N row-major 8x8 blocks, as embed / extract get it (tmf::top_column8):
+// sigma0, u0, and sweeps (+100 when the full cyclic routine was used instead of the dominant-column one)
+int hostsim_top_column(const float* blocks, int64_t n, float* sigma0, float* u0, int* sweeps) {
+  for (int64_t b = 0; b < n; ++b) {
+    float a[64];
+    std::memcpy(a, blocks + 64 * b, sizeof a);
+    sigma0[b] = top_column8(a, u0 + 8 * b, sweeps + b);
+  }
+  return 0;
+}
+
 int hostsim_dct(const float* in, float* out, int64_t n, int inverse) {
   for (int64_t b = 0; b < n; ++b) {
     float a[64];

@@ -62,6 +62,14 @@ def svd(blocks):
     return AV, V, S, sw
 
 
+def top_column(blocks):
+    blocks = np.ascontiguousarray(blocks, np.float32).reshape(-1, 8, 8)
+    n = len(blocks)
+    s0, u0, sw = np.empty(n, np.float32), np.empty((n, 8), np.float32), np.zeros(n, np.int32)
+    lib().hostsim_top_column(_p(blocks), C.c_int64(n), _p(s0), _p(u0), _p(sw))
+    return s0, u0, sw
+
+
 def dct(blocks, inverse=False):
     blocks = np.ascontiguousarray(blocks, np.float32).reshape(-1, 8, 8)
     out = np.empty_like(blocks)

@@ -203,3 +203,40 @@ def test_adversarial_block_families(family, mode):
         d = np.abs(out.astype(int) - ref.astype(int)).reshape(8, n, 8, 3).max(axis=(0, 2, 3))
         assert d[ok].max() <= 1, (family, alpha, int(d[ok].max()))
         assert np.abs(H.extract(ref, img, alpha, mode).astype(int) - O.extract_array(ref, img, alpha).astype(int)).max() <= 1
+
+
+def test_dominant_column_jacobi_against_float64():
+    """tmf::top_column8 - the SVD step of faithful embed / extract.  Blocks with a dominant column take the
+    7-rotation sweeps (certified: |p|^2 > 4 x the rest), the others the full cyclic routine; either way sigma0
+    and u0 must be the float64 ones to fp32 round-off.  Covers both paths, the limit of the certificate, a
+    dominant column that is not column 0, rank-1 and zero blocks."""
+    from scipy.fft import dctn
+    rng = np.random.default_rng(11)
+    blocks = []
+    for k in range(300):                                   # DCT of noise around a mean: eligible
+        blocks.append(dctn((rng.uniform(0.2, 0.9) + rng.normal(0, rng.uniform(0.0, 0.08), (8, 8))).clip(0, 1), norm="ortho"))
+    for k in range(300):                                   # constructed: ratio sigma1^2/sigma0^2 from 0.02 up to 0.6
+        U, _ = np.linalg.qr(rng.normal(size=(8, 8)))
+        G = rng.normal(size=(8, 8)) * rng.uniform(0.0, 0.25)
+        V, _ = np.linalg.qr(np.eye(8) + G - G.T)
+        r = rng.uniform(0.02, 0.6)
+        s = np.concatenate([[1.0, np.sqrt(r * 0.9)], np.sqrt(r * 0.1 / 6) * rng.random(6)])
+        D = (U * s) @ V.T * rng.uniform(0.3, 5.0)
+        blocks.append(D[:, rng.permutation(8)] if k % 2 else D)   # dominant column anywhere
+    for k in range(100):                                   # two comparable patches, sparse pixels: not eligible
+        b = np.zeros((8, 8))
+        r_, c_ = rng.integers(1, 8, 2)
+        b[:r_, :c_] = rng.uniform(0.1, 1); b[r_:, c_:] = rng.uniform(0.1, 1)
+        blocks.append(dctn(b, norm="ortho"))
+    blocks.append(np.outer(rng.normal(size=8), rng.normal(size=8)))   # rank 1
+    blocks.append(np.zeros((8, 8)))
+    B = np.array(blocks, np.float32)
+    s0, u0, sw = H.top_column(B)
+    assert (sw < 100).sum() >= 350 and (sw >= 100).sum() >= 100, "both paths must be exercised"
+    assert sw[sw < 100].max() <= 5, f"dominant-column path took {sw[sw < 100].max()} sweeps"
+    for k in range(len(B) - 1):
+        U, S, _ = np.linalg.svd(B[k].astype(np.float64))
+        assert abs(s0[k] - S[0]) <= 1e-6 * S[0], (k, s0[k], S[0], sw[k])
+        if S[1] < 0.9 * S[0]:                              # u0 is defined up to sign
+            assert min(np.abs(u0[k] - U[:, 0]).max(), np.abs(u0[k] + U[:, 0]).max()) <= 2e-4 / (1 - S[1] / S[0]), (k, sw[k])
+    assert s0[-1] == 0.0

@@ -224,18 +224,70 @@ __device__ __forceinline__ void dct2_smem(float* __restrict__ m, const float* __
 }
 
 // Cyclic one-sided Jacobi on the row-major N x N matrix m in shared memory: m <- m V, columns
-// mutually orthogonal on return (column k = sigma_k u_k).  Same rotation, skip rules, scaling
+// mutually orthogonal on return (column k = sigma_k u_k) - or, when one column dominates, only the largest column
+// is orthogonal to the rest (see inside).  Same rotation, skip rules, scaling
 // and stop rule as tmf::jacobi_svd8.  Returns the power-of-two `unscale` of the column norms.
 template <int N, int T>
 __device__ __forceinline__ float jacobi_smem(float* __restrict__ m) {
-  float frob2 = 0.0f;
+  // column norms: their sum scales the block, the largest may certify a dominant column
+  float frob2 = 0.0f, best = -1.0f;
+  int top = 0;
 #pragma unroll 1
-  for (int k = 0; k < N * N; ++k) frob2 = fmaf(m[k * T], m[k * T], frob2);
+  for (int j = 0; j < N; ++j) {
+    float sj = 0.0f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) sj = fmaf(m[(i * N + j) * T], m[(i * N + j) * T], sj);
+    frob2 += sj;
+    if (sj > best) { best = sj; top = j; }
+  }
   float unscale = 1.0f;
   if (!((frob2 > 0.0f) && (frob2 < INFINITY))) return unscale;
   const float sc = tmf::pow2_scale_for(frob2, unscale);
 #pragma unroll 1
   for (int k = 0; k < N * N; ++k) m[k * T] *= sc;
+
+  if (best > TMF_JACOBI_TOP_DOMINANCE * (frob2 - best)) {
+    // Dominant column only (tmf::top_column8 has the argument): p stays in registers and is rotated against
+    // each of the other N - 1 columns, N - 1 rotations per sweep instead of N (N - 1) / 2, until it is
+    // orthogonal to all of them.  The other columns are NOT mutually orthogonal on return; embed and
+    // extract read the largest column only.
+    float xp[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) xp[i] = m[(i * N + top) * T];
+#pragma unroll 1
+    for (int sweep = 0; sweep < TMF_JACOBI_MAX_SWEEPS + 4; ++sweep) {
+      float worst = 0.0f, al = 0.0f;
+#pragma unroll
+      for (int i = 0; i < N; ++i) al = fmaf(xp[i], xp[i], al);
+#pragma unroll 1
+      for (int q = 0; q < N; ++q) {
+        if (q == top) continue;
+        float xq[N], be = 0.0f, ga = 0.0f;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          xq[i] = m[(i * N + q) * T];
+          be = fmaf(xq[i], xq[i], be);
+          ga = fmaf(xp[i], xq[i], ga);
+        }
+        float c, s, t;
+        const float code = tmf::jacobi_cs(al, be, ga, c, s, &t, TMF_JACOBI_TOP_DONE * TMF_JACOBI_TOP_DONE);
+        worst = fmaxf(worst, code);
+        if (code > 0.0f) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            m[(i * N + q) * T] = fmaf(s, xp[i], c * xq[i]);
+            xp[i] = fmaf(c, xp[i], -s * xq[i]);
+          }
+          al = fmaxf(al - t * ga, 0.0f);
+        }
+      }
+      if (!(worst > TMF_JACOBI_MORE)) break;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) m[(i * N + top) * T] = xp[i];
+    return unscale;
+  }
+
 #pragma unroll 1
   for (int sweep = 0; sweep < TMF_JACOBI_MAX_SWEEPS + 4; ++sweep) {     // larger N: a few more sweeps
     float worst = 0.0f;

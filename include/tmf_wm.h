@@ -49,8 +49,10 @@ enum {
 
 /* `mode` of the fused kernels */
 enum {
-  TMF_MODE_FAITHFUL = 0, /* DCT -> full one-sided Jacobi SVD -> sigma0 += alpha*w -> U S' V^T -> IDCT,
-                            colour math bit-exact with the reference's float64 dot */
+  TMF_MODE_FAITHFUL = 0, /* DCT -> one-sided Jacobi for sigma0, u0 (rotations against the dominant column only
+                            when one is certified dominant, full cyclic sweeps otherwise) -> sigma0 += alpha*w ->
+                            U S' V^T (as the rank-1 identity below) -> IDCT; colour math bit-exact with the
+                            reference's float64 dot */
   TMF_MODE_FAST = 1,     /* algebraically reduced: top singular triplet of the spatial block and a
                             rank-1 update (orthonormal DCT preserves singular values; NO DCT and NO SVD
                             are executed); fp32 colour */

@@ -501,6 +501,73 @@ def test_other_block_sizes_vs_oracle(bs, mode):
         assert np.abs(got[k].astype(int) - O.embed_array(imgs[k], wms[k], 0.1, bs).astype(int)).max() <= 1
 
 
+def _adversarial_blocks(family, bs, n, rng):
+    """Blocks that stress the SVD step: near-tied top singular values, rank-deficient blocks, blocks without a
+    dominant column (the full-sweep fallback of tmf::top_column8) next to blocks with one."""
+    B = np.zeros((n, bs, bs), np.uint8)
+    for k in range(n):
+        if family == "two_pixels":
+            a = int(rng.integers(1, 256)); b = min(255, max(1, a + int(rng.integers(-3, 4))))
+            i, j = rng.choice(bs, 2, replace=False); p, q = rng.choice(bs, 2, replace=False)
+            B[k, i, p] = a; B[k, j, q] = b
+        elif family == "two_rectangles":
+            a, b = rng.integers(1, 256, 2); r, c = rng.integers(1, bs, 2)
+            B[k, :r, :c] = a; B[k, r:, c:] = b
+        elif family == "checker":
+            base = (np.add.outer(np.arange(bs), np.arange(bs)) % 2) * int(rng.integers(1, 256))
+            B[k] = np.clip(base + rng.integers(0, 3, (bs, bs)), 0, 255)
+        elif family == "stripes":
+            B[k, :, :: int(rng.integers(2, 4))] = int(rng.integers(1, 256))
+            B[k, int(rng.integers(0, bs))] = int(rng.integers(0, 256))
+        else:   # flat_noise
+            B[k] = np.clip(int(rng.integers(0, 256)) + rng.integers(-2, 3, (bs, bs)), 0, 255)
+    return np.repeat(B.transpose(1, 0, 2).reshape(bs, bs * n)[:, :, None], 3, axis=2).copy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("family", ["two_pixels", "two_rectangles", "checker", "stripes", "flat_noise"])
+def test_adversarial_block_families_on_the_gpu(family, mode):
+    """tests/test_hostsim.py runs these families through the host build of the arithmetic; here the kernels
+    themselves.  Every block whose two largest singular values differ by >= 1e-4 relative must match the
+    oracle to 1 LSB; sigma0 (extract) is well defined even at a tie."""
+    rng = np.random.default_rng(77)
+    n = 2048
+    img = _adversarial_blocks(family, 8, n, rng)
+    wm = rng.integers(1, 256, (1, n), dtype=np.uint8)
+    for alpha in (0.1, 1.0):
+        taps = {}
+        ref = O.embed_array(img, wm, alpha, taps=taps)
+        S = taps["S"][0]
+        ok = (S[:, 0] - S[:, 1]) >= 1e-4 * np.maximum(S[:, 0], 1e-30)
+        out = gpu_embed(img, wm, alpha, mode)
+        d = np.abs(out.astype(int) - ref.astype(int)).reshape(8, n, 8, 3).max(axis=(0, 2, 3))
+        assert d[ok].max() <= 1, (family, alpha, int(d[ok].max()))
+        ext = gpu_extract(ref, img, alpha, mode)
+        assert np.abs(ext.astype(int) - O.extract_array(ref, img, alpha).astype(int)).max() <= 1, (family, alpha)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bs", [6, 12, 16])
+@pytest.mark.parametrize("family", ["two_rectangles", "stripes", "flat_noise"])
+def test_adversarial_block_families_other_block_sizes(family, bs):
+    """The same for the generic-N faithful kernels (dominant-column path and its fallback in shared memory)."""
+    rng = np.random.default_rng(bs)
+    n = 512
+    img = _adversarial_blocks(family, bs, n, rng)
+    wm = rng.integers(1, 256, (1, n), dtype=np.uint8)
+    taps = {}
+    ref = O.embed_array(img, wm, 0.1, bs, taps=taps)
+    S = taps["S"][0]
+    ok = (S[:, 0] - S[:, 1]) >= 1e-4 * np.maximum(S[:, 0], 1e-30)
+    x = torch.from_numpy(img).cuda()
+    out = W.embed_tensor(x, torch.from_numpy(wm).cuda(), 0.1, bs, MODE_FAITHFUL).cpu().numpy()
+    d = np.abs(out.astype(int) - ref.astype(int)).reshape(bs, n, bs, 3).max(axis=(0, 2, 3))
+    assert d[ok].max() <= 1, (family, bs, int(d[ok].max()))
+    ext = W.extract_tensor(torch.from_numpy(ref).cuda(), x, 0.1, bs, MODE_FAITHFUL).cpu().numpy()
+    assert np.abs(ext.astype(int) - O.extract_array(ref, img, 0.1, bs).astype(int)).max() <= 1, (family, bs)
+
+
 def test_watermark_map_is_cached_per_device(golden):
     g = golden("pil_png_preserve1")
     png = g["png"].tobytes()

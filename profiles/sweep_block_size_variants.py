@@ -10,11 +10,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "thatsmyface_b200", "lib", "variants")
-VARIANTS = {          # earlier tables: r02_sweep_j_block_sizes.txt (rows ahead, CTAs per SM), r02_sweep_l (packed Gram)
-    "fn_default": {},
-    "fn_14c2": {"TMF_FASTN_CTAS_14": 2},
-    "fn_16c3": {"TMF_FASTN_CTAS_16": 3},
-    "fn_12c2": {"TMF_FASTN_CTAS_12": 2},
+VARIANTS = {          # earlier tables: r02_sweep_j (rows ahead, CTAs per SM), r02_sweep_l (packed Gram), r02_sweep_m (CTA size)
+    "fn_default": {},          # one-warp CTAs for 10 ... 16, 128 threads for 4 and 6
+    "fn_t128": {"TMF_FASTN_THREADS": 128, "TMF_FASTN_CTAS_10": 4, "TMF_FASTN_CTAS_12": 3, "TMF_FASTN_CTAS_14": 3, "TMF_FASTN_CTAS_16": 2},
 }
 SIZES = ["4", "6", "10", "12", "14", "16"]
 

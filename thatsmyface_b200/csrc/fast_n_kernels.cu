@@ -130,10 +130,10 @@ __device__ __forceinline__ void gram_of_block_n(const uint8_t* __restrict__ base
 }
 
 template <int N, int AL>
-__global__ void __launch_bounds__(kThreads, fastn_min_ctas<N>())
+__global__ void __launch_bounds__(fastn_threads<N>(), fastn_min_ctas<N>())
 k_embed_fast_n(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, BlockGeom g,
                const uint8_t* __restrict__ wm, int wm_shared, double alpha) {
-  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long gb = (long long)blockIdx.x * fastn_threads<N>() + threadIdx.x;
   if (gb >= g.total_blocks) return;
   long long img; int by, bx;
   uint32_t in_img;
@@ -189,10 +189,10 @@ __device__ __forceinline__ float sigma0_of_block_n(const uint8_t* __restrict__ b
 }
 
 template <int N, int AL>
-__global__ void __launch_bounds__(kThreads, fastn_min_ctas<N>())
+__global__ void __launch_bounds__(fastn_threads<N>(), fastn_min_ctas<N>())
 k_extract_fast_n(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ orig, uint8_t* __restrict__ out_wm,
                  BlockGeom g, double alpha) {
-  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long gb = (long long)blockIdx.x * fastn_threads<N>() + threadIdx.x;
   if (gb >= g.total_blocks) return;
   long long img; int by, bx;
   const size_t org = block_origin<N>(g, gb, img, by, bx);
@@ -208,9 +208,9 @@ k_extract_fast_n(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ or
 }
 
 template <int N, int AL>
-__global__ void __launch_bounds__(kThreads, fastn_min_ctas<N>())
+__global__ void __launch_bounds__(fastn_threads<N>(), fastn_min_ctas<N>())
 k_sigma0_fast_n(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, BlockGeom g) {
-  const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long gb = (long long)blockIdx.x * fastn_threads<N>() + threadIdx.x;
   if (gb >= g.total_blocks) return;
   long long img; int by, bx;
   const size_t org = block_origin<N>(g, gb, img, by, bx);
@@ -252,26 +252,26 @@ bool all16(const BlockGeom& g, const void* p0, const void* p1) {
 
 int launch_embed_fast_n(const uint8_t* rgb, uint8_t* out, const BlockGeom& g, const uint8_t* wm, int wm_shared,
                         double alpha, cudaStream_t st) {
-  const unsigned grid = grid_for(g.total_blocks, kThreads);
   for_block_size(g, row_alignment(g, rgb, out), [&](auto n_, auto a_) {
-    k_embed_fast_n<decltype(n_)::value, decltype(a_)::value><<<grid, kThreads, 0, st>>>(rgb, out, g, wm, wm_shared, alpha);
+    constexpr int N = decltype(n_)::value, T = fastn_threads<N>();
+    k_embed_fast_n<N, decltype(a_)::value><<<grid_for(g.total_blocks, T), T, 0, st>>>(rgb, out, g, wm, wm_shared, alpha);
   }, all16(g, rgb, out));
   return check_launch("embed kernel launch");
 }
 
 int launch_extract_fast_n(const uint8_t* wmk, const uint8_t* orig, uint8_t* out_wm, const BlockGeom& g, double alpha,
                           cudaStream_t st) {
-  const unsigned grid = grid_for(g.total_blocks, kThreads);
   for_block_size(g, row_alignment(g, wmk, orig), [&](auto n_, auto a_) {
-    k_extract_fast_n<decltype(n_)::value, decltype(a_)::value><<<grid, kThreads, 0, st>>>(wmk, orig, out_wm, g, alpha);
+    constexpr int N = decltype(n_)::value, T = fastn_threads<N>();
+    k_extract_fast_n<N, decltype(a_)::value><<<grid_for(g.total_blocks, T), T, 0, st>>>(wmk, orig, out_wm, g, alpha);
   }, all16(g, wmk, orig));
   return check_launch("extract kernel launch");
 }
 
 int launch_sigma0_fast_n(const uint8_t* rgb, float* sigma0, const BlockGeom& g, cudaStream_t st) {
-  const unsigned grid = grid_for(g.total_blocks, kThreads);
   for_block_size(g, row_alignment(g, rgb, rgb), [&](auto n_, auto a_) {
-    k_sigma0_fast_n<decltype(n_)::value, decltype(a_)::value><<<grid, kThreads, 0, st>>>(rgb, sigma0, g);
+    constexpr int N = decltype(n_)::value, T = fastn_threads<N>();
+    k_sigma0_fast_n<N, decltype(a_)::value><<<grid_for(g.total_blocks, T), T, 0, st>>>(rgb, sigma0, g);
   }, all16(g, rgb, rgb));
   return check_launch("sigma0 kernel launch");
 }

@@ -131,6 +131,9 @@ __device__ __forceinline__ void embed_row_n(const uint32_t (&w)[kRowWords<N>], c
   for (int k = 0; k < NW; ++k) o[k] = tmf::pack4_sat_u8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
 }
 
+// threads per CTA: one-warp CTAs for the register-heavy sizes (10 ... 16: +1-3 %), 128 for 4 and 6 (one-warp CTAs
+// cost size 4 8 % of its extract rate)
+template <int N> __host__ __device__ constexpr int fastn_threads() { return N <= 6 ? 128 : TMF_FASTN_THREADS; }
 template <int N> __host__ __device__ constexpr int fastn_min_ctas() {
   return N <= 6 ? TMF_FASTN_CTAS_SMALL : (N <= 10 ? TMF_FASTN_CTAS_10 : (N <= 12 ? TMF_FASTN_CTAS_12 : (N <= 14 ? TMF_FASTN_CTAS_14 : TMF_FASTN_CTAS_16)));
 }

@@ -46,22 +46,26 @@
 #define TMF_FAITHFUL_R1_MIN_CTAS 3
 #endif
 
-// generic-N fast kernels (fast_n_kernels.cu): minimum CTAs of 128 threads per SM by block size
-// (4, 6 | 10 | 12 | 14 | 16); the Gram matrix alone is N (N + 1) / 2 registers
+// generic-N fast kernels (fast_n_kernels.cu): threads per CTA for sizes 10 ... 16 (4 and 6 run 128) and minimum
+// CTAs per SM by block size (4, 6 | 10 | 12 | 14 | 16); the Gram matrix alone is N (N + 1) / 2 registers
+#ifndef TMF_FASTN_THREADS
+#define TMF_FASTN_THREADS 32
+#endif
 #ifndef TMF_FASTN_CTAS_SMALL
 #define TMF_FASTN_CTAS_SMALL 6
 #endif
 #ifndef TMF_FASTN_CTAS_10
-#define TMF_FASTN_CTAS_10 4
+#define TMF_FASTN_CTAS_10 16       // 128 registers
 #endif
 #ifndef TMF_FASTN_CTAS_12
-#define TMF_FASTN_CTAS_12 3
+#define TMF_FASTN_CTAS_12 12       // 168 registers
 #endif
 #ifndef TMF_FASTN_CTAS_14
-#define TMF_FASTN_CTAS_14 3        // 168 registers: a few spilled words, but 12 warps per SM (extract 557 k -> 621 k MP/s)
+#define TMF_FASTN_CTAS_14 12       // 168 registers and a few spilled words; at 8 (223 registers, no spill) extract is 10 % slower
+                                   // (the register file is per scheduler: 9-12 warps per SM all mean 168 registers)
 #endif
 #ifndef TMF_FASTN_CTAS_16
-#define TMF_FASTN_CTAS_16 2        // 255 registers: the 136-entry Gram matrix and a row ahead, no spill (3 spills 1 KB: 0.68x)
+#define TMF_FASTN_CTAS_16 8        // 255 registers: the 136-entry Gram matrix and a row ahead, no spill
 #endif
 // ... and the largest block size whose row loops fetch one row ahead (a second row of registers)
 #ifndef TMF_FASTN_ROWS_AHEAD_MAX_N

@@ -287,9 +287,6 @@ TMF_HD void idct8x8(float* a) {
 //
 // Returns the number of sweeps that performed at least one rotation.
 // ---------------------------------------------------------------------------
-#ifndef TMF_JACOBI_F32X2
-#define TMF_JACOBI_F32X2 1             // packed-fp32 rounds on the device (0: scalar rounds)
-#endif
 #define TMF_JACOBI_TOL 1.0e-6f
 #define TMF_JACOBI_DONE 1.0e-3f        // see the stop rule below
 #define TMF_JACOBI_MORE 1.5f          // jacobi_cs returned 2 for some pair of the sweep
@@ -491,7 +488,7 @@ TMF_HD int jacobi_svd8(float* a, float* v, float& unscale) {
   }
   int sweeps = 0;
   bool more = live;
-#if defined(__CUDA_ARCH__) && TMF_JACOBI_F32X2
+#if defined(__CUDA_ARCH__)   // packed-fp32 rounds on the device, scalar ones on the host (tests/hostsim)
   // pack row pairs (register renaming), iterate, unpack
   float2 a2[32], v2[WITH_V ? 32 : 1];
 #pragma unroll
@@ -604,7 +601,7 @@ TMF_HD float top_column8(float* a, float* u, int* sweeps) {
     }
     int sw = 0;
     bool more = true;
-#if defined(__CUDA_ARCH__) && TMF_JACOBI_F32X2
+#if defined(__CUDA_ARCH__)   // packed-fp32 rounds on the device, scalar ones on the host (tests/hostsim)
     float2 a2[32];
 #pragma unroll
     for (int rp = 0; rp < 4; ++rp)

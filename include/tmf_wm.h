@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define TMF_VERSION 200 /* 0.2.0: TMF_MODE_LITERAL, tmf_last_fast_path, faithful mode at every block size */
+#define TMF_VERSION 201 /* 0.2.1: + tmf_wm_map_axis_table (0.2.0: TMF_MODE_LITERAL, tmf_last_fast_path, faithful mode at every block size) */
 
 enum {
   TMF_OK = 0,

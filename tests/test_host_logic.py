@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.tmf_version() == 200
+    assert lib.tmf_version() == 201
 
 
 def test_argument_validation_happens_before_any_cuda_work(lib):

@@ -144,7 +144,7 @@ k_embed_faithful(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ out, Blo
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kThreads, TMF_FAITHFUL_R1_MIN_CTAS)
+__global__ void __launch_bounds__(kThreads, TMF_FAITHFUL_SIGMA_MIN_CTAS)
 k_extract_faithful(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ orig, uint8_t* __restrict__ out_wm,
                    BlockGeom g, double alpha) {
   const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -167,7 +167,7 @@ k_extract_faithful(const uint8_t* __restrict__ wmk, const uint8_t* __restrict__ 
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kThreads, TMF_FAITHFUL_R1_MIN_CTAS)
+__global__ void __launch_bounds__(kThreads, TMF_FAITHFUL_SIGMA_MIN_CTAS)
 k_sigma0_faithful(const uint8_t* __restrict__ rgb, float* __restrict__ sigma0, BlockGeom g) {
   const long long gb = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (gb >= g.total_blocks) return;

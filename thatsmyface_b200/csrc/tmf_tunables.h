@@ -37,13 +37,17 @@
 #define TMF_TILE_CTAS_PER_SM 1
 #endif
 
-// faithful kernels, block size 8: minimum CTAs of 128 threads per SM - the literal form (A and V
-// in registers) and the default form / extract / sigma0 (A only)
+// faithful kernels, block size 8: minimum CTAs of 128 threads per SM - the literal form (A and V in registers),
+// the default embed (A only; since the dominant-column Jacobi 128 registers with 196 spilled bytes beat 168 with 60:
+// 181 k -> 186 k MP/s) and extract / sigma0 (80 registers: 210 k -> 253 k MP/s; 248 k at 5 x 128 threads, 238 k at 4)
 #ifndef TMF_FAITHFUL_MIN_CTAS
 #define TMF_FAITHFUL_MIN_CTAS 3
 #endif
 #ifndef TMF_FAITHFUL_R1_MIN_CTAS
-#define TMF_FAITHFUL_R1_MIN_CTAS 3
+#define TMF_FAITHFUL_R1_MIN_CTAS 4
+#endif
+#ifndef TMF_FAITHFUL_SIGMA_MIN_CTAS
+#define TMF_FAITHFUL_SIGMA_MIN_CTAS 6
 #endif
 
 // generic-N fast kernels (fast_n_kernels.cu): threads per CTA for sizes 10 ... 16 (4 and 6 run 128) and minimum

@@ -38,13 +38,13 @@
 #endif
 
 // faithful kernels, block size 8: minimum CTAs of 128 threads per SM - the literal form (A and V in registers),
-// the default embed (A only; since the dominant-column Jacobi 128 registers with 196 spilled bytes beat 168 with 60:
-// 181 k -> 186 k MP/s) and extract / sigma0 (80 registers: 210 k -> 253 k MP/s; 248 k at 5 x 128 threads, 238 k at 4)
+// the default embed (A only; 4 CTAs = 128 registers with 196 spilled bytes measured 186 k against 181 k MP/s alone but
+// 161 k against 169-180 k inside bench.py under the power cap: left at 3) and extract / sigma0 (80 registers: 210 k -> 253 k MP/s; 248 k at 5 x 128 threads, 238 k at 4)
 #ifndef TMF_FAITHFUL_MIN_CTAS
 #define TMF_FAITHFUL_MIN_CTAS 3
 #endif
 #ifndef TMF_FAITHFUL_R1_MIN_CTAS
-#define TMF_FAITHFUL_R1_MIN_CTAS 4
+#define TMF_FAITHFUL_R1_MIN_CTAS 3
 #endif
 #ifndef TMF_FAITHFUL_SIGMA_MIN_CTAS
 #define TMF_FAITHFUL_SIGMA_MIN_CTAS 6

@@ -57,7 +57,7 @@ __device__ __forceinline__ void gram_of_block(const uint8_t* __restrict__ base0,
     float2 y2[4];
     if (kRunning) { load_row24<VEC>(base, w); base += pitch; }
     else load_row24<VEC>(base0 + (size_t)i * pitch, w);
-    row_luma2(w, y2);
+    row_luma2<KEEP == 0 && TMF_EXTRACT_I2F>(w, y2);
     if (KEEP == 2) {
 #pragma unroll
       for (int p = 0; p < 4; ++p) col[(4 * i + p) * STRIDE] = y2[p];

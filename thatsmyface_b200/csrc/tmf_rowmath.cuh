@@ -49,25 +49,36 @@ __device__ __forceinline__ uint32_t dp2a_hi(uint32_t bytes, uint32_t w16x2, uint
   return d;
 }
 // magic float 2^23 + (299 r + 587 g + 114 b) of pixel j of the row
-__device__ __forceinline__ float pixel_luma_magic(const uint32_t (&w)[6], int j) {
+template <uint32_t ACC0 = 0x4B000000u>
+__device__ __forceinline__ uint32_t pixel_luma_bits(const uint32_t (&w)[6], int j) {
   constexpr uint32_t kRG = 299u | (587u << 16), kB_ = 114u, k_R = 299u << 16, kGB = 587u | (114u << 16);
   const int k = (3 * j) >> 2;
   uint32_t m;
   switch ((3 * j) & 3) {
-    case 0: m = dp2a_hi(w[k], kB_, dp2a_lo(w[k], kRG, 0x4B000000u)); break;          // [r g b .]
-    case 1: m = dp2a_hi(w[k], kGB, dp2a_lo(w[k], k_R, 0x4B000000u)); break;          // [. r g b]
-    case 2: m = dp2a_lo(w[k + 1], kB_, dp2a_hi(w[k], kRG, 0x4B000000u)); break;      // [. . r g][b . . .]
-    default: m = dp2a_lo(w[k + 1], kGB, dp2a_hi(w[k], k_R, 0x4B000000u)); break;     // [. . . r][g b . .]
+    case 0: m = dp2a_hi(w[k], kB_, dp2a_lo(w[k], kRG, ACC0)); break;          // [r g b .]
+    case 1: m = dp2a_hi(w[k], kGB, dp2a_lo(w[k], k_R, ACC0)); break;          // [. r g b]
+    case 2: m = dp2a_lo(w[k + 1], kB_, dp2a_hi(w[k], kRG, ACC0)); break;      // [. . r g][b . . .]
+    default: m = dp2a_lo(w[k + 1], kGB, dp2a_hi(w[k], k_R, ACC0)); break;     // [. . . r][g b . .]
   }
-  return __uint_as_float(m);
+  return m;
+}
+__device__ __forceinline__ float pixel_luma_magic(const uint32_t (&w)[6], int j) {
+  return __uint_as_float(pixel_luma_bits(w, j));
 }
 #define TMF_LUMA_UNIT TMF_LUMA1000_UNIT
 
-// luma of the 8 pixels of a row as four pairs; same values as tmf::luma1000_exact
+// luma of the 8 pixels of a row as four pairs; same values as tmf::luma1000_exact.  CONVERT: the integer goes
+// through I2F (the conversion pipe, idle in the FAST kernels) instead of the magic-number FADD2 (the FMA pipe) -
+// for a kernel bound by the FMA pipe rather than by issue slots.
+template <bool CONVERT = false>
 __device__ __forceinline__ void row_luma2(const uint32_t (&w)[6], float2 (&y2)[4]) {
 #pragma unroll
-  for (int p = 0; p < 4; ++p)
-    y2[p] = __fadd2_rn(make_float2(pixel_luma_magic(w, 2 * p), pixel_luma_magic(w, 2 * p + 1)), bc2(-8388608.0f));
+  for (int p = 0; p < 4; ++p) {
+    if (CONVERT)
+      y2[p] = make_float2(__uint2float_rn(pixel_luma_bits<0u>(w, 2 * p)), __uint2float_rn(pixel_luma_bits<0u>(w, 2 * p + 1)));
+    else
+      y2[p] = __fadd2_rn(make_float2(pixel_luma_magic(w, 2 * p), pixel_luma_magic(w, 2 * p + 1)), bc2(-8388608.0f));
+  }
 }
 
 // Gram matrix in paired form: gp[i][p] = (G[i][2p], G[i][2p+1]) for the pairs of the

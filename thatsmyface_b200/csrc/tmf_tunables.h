@@ -24,6 +24,9 @@
 #ifndef TMF_EXTRACT_THREADS
 #define TMF_EXTRACT_THREADS 32
 #endif
+#ifndef TMF_EXTRACT_I2F
+#define TMF_EXTRACT_I2F 1        // extract / sigma0: luma integers to float by I2F (conversion pipe) instead of FADD2
+#endif
 #ifndef TMF_FAST_MIN_CTAS
 #define TMF_FAST_MIN_CTAS 6      // extract / sigma0: 80 registers
 #endif

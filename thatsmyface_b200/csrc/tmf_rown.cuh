@@ -35,7 +35,6 @@ __device__ __forceinline__ void row_luma_n(const uint32_t (&w)[kRowWords<N>], fl
   }
 }
 
-// byte B of the row as the subnormal float B * 2^-149 (bit pattern = the byte)
 // the same as pairs (y_2p, y_2p+1), as the packed Gram update below wants them
 template <int N>
 __device__ __forceinline__ void row_luma2_n(const uint32_t (&w)[kRowWords<N>], float2 (&y2)[N / 2]) {
@@ -85,6 +84,7 @@ __device__ __forceinline__ void gram_pairs_to_sym_n(const GramPairsN<N>& G, floa
   }
 }
 
+// byte B of the row as the subnormal float B * 2^-149 (bit pattern = the byte)
 template <int NW>
 __device__ __forceinline__ float byte_subnormal_n(const uint32_t (&w)[NW], int B) {
   const uint32_t x = w[B >> 2];

@@ -160,3 +160,23 @@ def test_watermark_map_cache_and_decoding_helper(golden):
     big = W.prepare_for_decoding(Image.fromarray(a), scale=4, border=16)
     assert big.mode == "L" and big.size == (25 * 4 + 32, 16 * 4 + 32)
     assert set(np.unique(np.array(big))) <= {0, 255}
+
+
+def test_hot_kernels_keep_their_matrices_in_registers():
+    """ptxas resource usage of the built library (thatsmyface_b200.build keeps the -v logs): the tile kernel and the
+    generic-N kernels up to 12 must have no stack frame.  A rolled loop once indexed the Gram matrix dynamically and
+    pinned it to local memory (153 STL per block on the hot path, block sizes 10-16 at 0.3-0.4 of the roofline)."""
+    from thatsmyface_b200 import build as B
+    rows = B.resource_report()
+    if not rows:
+        pytest.skip("no ptxas logs beside the objects (library built elsewhere)")
+    by_name = {r[0]: r for r in rows}
+    tile = [r for n, r in by_name.items() if n.startswith("k_embed_tile<")]
+    assert tile and all(r[2] == 0 and r[1] <= 128 for r in tile), tile
+    for n, r in by_name.items():
+        if n.startswith(("k_embed_fast_n<", "k_extract_fast_n<", "k_sigma0_fast_n<")):
+            size = int(n.split("<")[1].split(",")[0])
+            if size <= 12:
+                assert r[2] == 0, f"{n}: {r[2]} bytes of stack frame"
+        if n in ("k_embed_fast<8>", "k_sigma0_fast<8>"):
+            assert r[2] == 0, (n, r)

@@ -96,16 +96,21 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
     def flags_for(src: str):
         text = "".join(open(p).read() for p in _closure(os.path.join(CSRC, src)) if not p.endswith("tmf_tunables.h"))
         used = [d for d in defines if d.split("=")[0] in text]
-        return NVCC_FLAGS + [f"-D{d}" for d in used] + (["-Xptxas", "-v"] if verbose else [])
+        return NVCC_FLAGS + [f"-D{d}" for d in used] + ["-Xptxas", "-v"]
 
     def compile_one(src: str) -> str:
         flags = flags_for(src)
         obj = os.path.join(OBJDIR, f"{os.path.splitext(src)[0]}.{_key(src, flags)}.o")
-        if os.path.exists(obj) and not verbose and not force:
+        log = obj[:-2] + ".ptxas.txt"        # registers / stack / spills of every kernel (resource_report)
+        if os.path.exists(obj) and os.path.exists(log) and not force:
+            if verbose:
+                print(open(log).read())
             return obj
         res = subprocess.run([nvcc] + flags + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        with open(log, "w") as f:
+            f.write(res.stderr)
         if verbose:
             print(res.stderr)
         return obj
@@ -115,15 +120,49 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
     res = subprocess.run([nvcc, "-shared", "-o", out] + objs + ["-lcudart"], capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+    if out == LIBPATH:                       # which objects the default library was linked from
+        with open(os.path.join(LIBDIR, "linked_objects.txt"), "w") as f:
+            f.write("\n".join(objs) + "\n")
     # keep the cache small: drop objects no current source/flag combination refers to, oldest first
     cached = sorted(glob.glob(os.path.join(OBJDIR, "*.o")), key=os.path.getmtime)
     for p in cached[:-64]:
-        try:
-            os.remove(p)
-        except OSError:
-            pass
+        for q in (p, p[:-2] + ".ptxas.txt"):
+            try:
+                os.remove(q)
+            except OSError:
+                pass
     return out
 
+
+def resource_report() -> list:
+    """(kernel, registers, stack bytes, spill-store bytes, spill-load bytes) of every kernel of the default library,
+    from the ptxas -v logs kept beside its objects."""
+    import subprocess as sp
+    rows = []
+    listing = os.path.join(LIBDIR, "linked_objects.txt")
+    if not os.path.exists(listing):
+        build()
+    for obj in open(listing).read().split():
+        log = obj[:-2] + ".ptxas.txt"
+        if not os.path.exists(log):
+            continue
+        text = open(log).read()
+        for m in re.finditer(r"Compiling entry function '(\S+)' for 'sm_100a'\s*\n.*?\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, "
+                             r"(\d+) bytes spill loads\s*\n.*?Used (\d+) registers", text):
+            rows.append((m.group(1), int(m.group(5)), int(m.group(2)), int(m.group(3)), int(m.group(4))))
+    names = sp.run(["c++filt"], input="\n".join(r[0] for r in rows), capture_output=True, text=True).stdout.split("\n")
+    out_rows = []
+    for r, n in zip(rows, names):
+        n = re.sub(r"tmfi::\(anonymous namespace\)::", "", n)
+        n = re.sub(r"\(.*$", "", n).replace("void ", "")
+        out_rows.append((n,) + r[1:])
+    return sorted(set(out_rows))
+
+
+if __name__ == "__main__" and "--resources" in sys.argv:
+    for row in resource_report():
+        print("%-48s regs %3d  stack %5d  spill st %5d ld %5d" % row)
+    sys.exit(0)
 
 if __name__ == "__main__":
     defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]

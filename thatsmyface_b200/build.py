@@ -141,7 +141,7 @@ def resource_report() -> list:
     rows = []
     listing = os.path.join(LIBDIR, "linked_objects.txt")
     if not os.path.exists(listing):
-        build()
+        return rows                           # a library built elsewhere (or before the logs were kept)
     for obj in open(listing).read().split():
         log = obj[:-2] + ".ptxas.txt"
         if not os.path.exists(log):

@@ -102,9 +102,19 @@ __device__ __forceinline__ void embed_row_n(const uint32_t (&w)[kRowWords<N>], c
   constexpr int NW = kRowWords<N>;
   float du = c;
   if (marked) {
-    float y[N];
-    row_luma_n<N>(w, y);
-    du = fmaf(f, tmf::dotn<N>(y, wv), c);
+    // z = row . w with two packed accumulators (four independent chains of N / 4 instead of one of N: with 2-3 warps
+    // per scheduler the chain's latency is exposed).  The order differs from tmf::dotn by rounding only, in a term
+    // that is scaled by f ~ 1e-3 - far below the quantiser's resolution, as in the block-8 kernels.
+    float2 y2[N / 2];
+    row_luma2_n<N>(w, y2);
+    float2 a0 = __fmul2_rn(y2[0], make_float2(wv[0], wv[1]));
+    float2 a1 = __fmul2_rn(y2[1], make_float2(wv[2], wv[3]));
+#pragma unroll
+    for (int p = 2; p < N / 2; ++p) {
+      if (p & 1) a1 = __ffma2_rn(y2[p], make_float2(wv[2 * p], wv[2 * p + 1]), a1);
+      else a0 = __ffma2_rn(y2[p], make_float2(wv[2 * p], wv[2 * p + 1]), a0);
+    }
+    du = fmaf(f, (a0.x + a0.y) + (a1.x + a1.y), c);
   }
   du *= 1.7763568394002505e-15f;   // 2^-49
   int q[4 * NW];

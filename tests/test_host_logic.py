@@ -180,3 +180,20 @@ def test_hot_kernels_keep_their_matrices_in_registers():
                 assert r[2] == 0, f"{n}: {r[2]} bytes of stack frame"
         if n in ("k_embed_fast<8>", "k_sigma0_fast<8>"):
             assert r[2] == 0, (n, r)
+
+
+def test_division_by_255_without_a_division_is_exact_for_every_byte():
+    """tmf::modulate_sigma0 computes wm / 255.0 as q + fma(-q, 255, k) * r with r = RN(1/255), q = RN(k r).
+    Emulated here with exact rationals (an fma is one rounding of the exact value): it must equal IEEE k / 255.0
+    for all 256 bytes, and the test must be able to fail (the plain product is wrong for some bytes)."""
+    from fractions import Fraction as F
+    r = 1.0 / 255.0
+    fma = lambda a, b, c: float(F(a) * F(b) + F(c))
+    plain_wrong = 0
+    for k in range(256):
+        kd = float(k)
+        q = kd * r
+        got = fma(fma(-q, 255.0, kd), r, q)
+        assert got == kd / 255.0, k
+        plain_wrong += q != kd / 255.0
+    assert plain_wrong > 0

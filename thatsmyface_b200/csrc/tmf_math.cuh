@@ -61,13 +61,6 @@ TMF_HD double d_add(double a, double b) {
   volatile double r = a + b; return r;
 #endif
 }
-TMF_HD double d_div(double a, double b) {
-#if defined(__CUDA_ARCH__)
-  return __ddiv_rn(a, b);
-#else
-  return a / b;
-#endif
-}
 TMF_HD float f_sqrt(float x) {
 #if defined(__CUDA_ARCH__)
   return __fsqrt_rn(x);
@@ -694,7 +687,13 @@ TMF_HD float top_column8(float* a, float* u, int* sweeps) {
 // watermarking.py:198 - S[0] += alpha * (wm / 255.0): float32 + float64 product,
 // float64 sum stored back to float32.
 TMF_HD float modulate_sigma0(float s0, double alpha, uint32_t wm_u8) {
-  const double w = d_div((double)wm_u8, 255.0);
+  // w = wm / 255.0 (float64 division, :198) without the division sequence (reciprocal seed, Newton steps, range
+  // check, slow-path call: ~12 instructions per block): with r = RN(1 / 255), q = k r, e = fma(-q, 255, k),
+  // q + e r is the correctly rounded quotient for every byte k (all 256 checked with exact rational arithmetic,
+  // tests/test_host_logic.py; the plain product k r alone is wrong for 24 of them)
+  const double k = (double)wm_u8, r = 1.0 / 255.0;
+  const double q = d_mul(k, r);
+  const double w = d_fma(d_fma(-q, 255.0, k), r, q);
   return (float)((double)s0 + d_mul(alpha, w));
 }
 
